@@ -1,0 +1,189 @@
+/* svr_b200 -- C ABI of the B200-native IF-Net implicit query path.
+ *
+ * Drop-in boundary for the hot path of nihalsid/single-view-3d-reconstruction:
+ * model/projection.py (depth -> point cloud -> voxel occupancy) and model/ifnet.py (multi-scale
+ * trilinear sampling + pointwise MLP decoder, forward and backward).  The reference has no FFI of
+ * its own for this path (it is pure PyTorch); each entry point below names the reference
+ * function (file:line, relative to the reference root) whose device work it replaces.  The
+ * reference-side binding is the ctypes stub in single-view-3d-reconstruction_b200/_abi.py
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; sizes are element counts;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *  - return value: 0 = ok, <0 = invalid argument, >0 = cudaError_t of a failed launch; the
+ *    message is available from svr_last_error() (thread-local);
+ *  - there is NO CPU fallback: a missing device, a non-sm_100 device or a failed launch is an error;
+ *  - bf16 buffers are passed as uint16_t*.
+ */
+#ifndef SVR_B200_H
+#define SVR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVR_ABI_VERSION 1
+#define SVR_MAX_LEVELS 6
+#define SVR_MAX_TAPS 15
+
+int svr_abi_version(void);
+const char *svr_last_error(void);
+/* 0 when the current device is compute capability 10.x; fills name (<=256 bytes) and SM count */
+int svr_device_info(char *name_host, int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Projection (model/projection.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* project.depth_to_camera (projection.py:201-206) + depthmap_to_gridspace (:150-163) [+ optional
+ * norm_grid_space (:124-132)] fused: depth (B,H,W) fp32 -> pts (B,H*W,3) fp32.
+ * cam = ((u*d - cx*d)/f, -((v*d - cy*d)/f), d);  g_k = fl(fl(scale[k]*cam_k) + offset[k]);
+ * if normalise: g_k = fl(fl(g_k - dims[k]/2) / dims[k]).  Bit-exact to the reference CPU path.
+ * grad version: d depth from d pts (same map, linear in d).                                     */
+int svr_unproject_fwd(const float *depth, int B, int H, int W, float f, float cx, float cy,
+                      const float *scale3_host, const float *offset3_host, const int64_t *dims3_host,
+                      int normalise, float *pts, void *stream);
+int svr_unproject_bwd(const float *grad_pts, int B, int H, int W, float f, float cx, float cy,
+                      const float *scale3_host, const int64_t *dims3_host, int normalise,
+                      float *grad_depth, void *stream);
+
+/* project.norm_grid_space (projection.py:124-132), in place on pts (n_points,3).               */
+int svr_norm_grid_space(float *pts, int64_t n_points, const int64_t *dims3_host, void *stream);
+
+/* project.pc_voxels (projection.py:39-80): trilinear splat of B*N normalised points into a dense
+ * (B,D0,D1,D2) fp32 grid, x8 sequential self-sum, clamp(0,1).  Bit-exact to the reference's
+ * serial (deterministic-mode) accumulation order: pass-major (k,j,i), then point index.
+ * No floating-point atomics: points are bucketed by floor cell with integer counters, every
+ * touched voxel is summed by exactly one thread in reference order.
+ *   tail_start : flat output index from which the 8-fold self-sum uses ATen's row_sum
+ *                association ((2a+2a)+2a)+2a instead of the sequential one (see
+ *                oracle/svr_oracle.c); pass B*D0*D1*D2 (or <0) for the canonical order.
+ *   sat_mask   : optional (may be NULL) bitmask, 1 bit per output voxel (ceil(B*V/32) words), set
+ *                where the pre-clamp value exceeds 1 (needed by svr_voxelize_bwd).
+ *   workspace  : svr_voxelize_workspace_bytes(B,N,dims) bytes of scratch.                        */
+size_t svr_voxelize_workspace_bytes(int B, int N, const int64_t *dims3_host);
+int svr_voxelize_fwd(const float *pts, int B, int N, const int64_t *dims3_host, double eps,
+                     int64_t tail_start, float *grid, uint32_t *sat_mask, void *workspace,
+                     size_t workspace_bytes, void *stream);
+/* backward of pc_voxels w.r.t. the points: d update = 8 * grad_grid * [pre-clamp <= 1], product
+ * rule over the three axis weights, times (dims[k]-1).  grad_pts (B,N,3) is overwritten.        */
+int svr_voxelize_bwd(const float *pts, const float *grad_grid, const uint32_t *sat_mask, int B, int N,
+                     const int64_t *dims3_host, double eps, float *grad_pts, void *stream);
+
+/* project.voxels_smooth (projection.py:102-117): three zero-padded 1-D cross-correlations (taps_w
+ * on the last axis, taps_h on the middle one, taps_d on the first), then clamp(0,1).
+ * The taps are DEVICE arrays (no host sync).  tmp0/tmp1: two scratch grids of the same size as
+ * `in`.  Odd tap counts <= SVR_MAX_TAPS.                                                         */
+int svr_blur_fwd(const float *in, int B, int D, int H, int W, const float *taps_w, int kw,
+                 const float *taps_h, int kh, const float *taps_d, int kd, float *out,
+                 float *tmp0, float *tmp1, void *stream);
+/* backward: grad_in (same shape) and grad_taps (kw+kh+kd floats, device, [w|h|d]) from grad_out.
+ * tmp: FOUR scratch grids.                                                                      */
+int svr_blur_bwd(const float *in, const float *grad_out, int B, int D, int H, int W,
+                 const float *taps_w, int kw, const float *taps_h, int kh,
+                 const float *taps_d, int kd, float *grad_in, float *grad_taps, float *tmp,
+                 void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * IF-Net sampling + decoder (model/ifnet.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Static description of the sampled feature pyramid (IFNetFeatureExtractor128 ifnet.py:122-199,
+ * IFNetFeatureExtractor ifnet.py:64-120).  Level 0 is the input grid itself (C = 1, fp32); levels
+ * >= 1 are packed channel-last bf16 volumes (svr_pack_volume).                                  */
+typedef struct svr_pyramid {
+    int n_levels;                     /* 6 (128-net) or 4 (32-net)                               */
+    int channels[SVR_MAX_LEVELS];     /* level 0 must be 1; others multiples of 8                */
+    int dims[SVR_MAX_LEVELS][3];      /* (D,H,W) of each level                                   */
+    int align_corners;                /* 0: 128-net (ifnet.py:162), 1: 32-net (ifnet.py:98)      */
+    float displacement;               /* 0.0722 (ifnet.py:144) / 0.035 (ifnet.py:82)             */
+} svr_pyramid;
+
+/* Padded K' (multiple of 64) of the permuted feature axis for a pyramid.                        */
+int svr_feature_kp(const svr_pyramid *pyr_host);
+
+/* fp32 volume with arbitrary element strides (B,C,D,H,W) -> bf16 NDHWC contiguous.              */
+int svr_pack_volume(const float *src, int B, int C, int D, int H, int W, int64_t sB, int64_t sC,
+                    int64_t sD, int64_t sH, int64_t sW, uint16_t *dst, void *stream);
+/* fp32 NDHWC contiguous gradient -> accumulate (+=) into fp32 tensor with arbitrary strides.    */
+int svr_unpack_volume_grad(const float *src_ndhwc, int B, int C, int D, int H, int W, int64_t sB,
+                           int64_t sC, int64_t sD, int64_t sH, int64_t sW, float *dst, int accumulate,
+                           void *stream);
+
+/* fc_0 weight (H0, 7*sum C) fp32 with k = c*7+d (ifnet.py:43-45) -> bf16 (H0, KP) in the
+ * permuted/padded K' order used by the kernels, and its transpose (KP, H0).  Either output may
+ * be NULL.  svr_unpack_w0_grad maps a (H0,KP) fp32 gradient back to (H0, 7*sum C).              */
+int svr_pack_w0(const float *w0, int H0, const svr_pyramid *pyr_host, uint16_t *w0p, uint16_t *w0pT,
+                void *stream);
+int svr_unpack_w0_grad(const float *gw0p, int H0, const svr_pyramid *pyr_host, float *gw0, void *stream);
+/* generic fp32 (R,C) -> bf16 (R,C) and/or its transpose (C,R)                                   */
+int svr_pack_matrix(const float *w, int R, int C, uint16_t *wp, uint16_t *wpT, void *stream);
+
+/* Multi-scale trilinear stencil gather (ifnet.py:156-197 == 6x F.grid_sample + cat, fused):
+ * points (B,N,3) fp32, x0 (B,D,H,W) fp32, vols[l] bf16 NDHWC for l>=1  ->  feat (B*N, KP) bf16 in
+ * K' order.                                                                                     */
+int svr_gather_fwd(const float *points, int B, int N, const float *x0, const uint16_t *const *vols_host,
+                   const svr_pyramid *pyr_host, uint16_t *feat, void *stream);
+/* Backward of the gather: dfeat (B*N, KP) bf16 -> scatter-add into gvols[l] (fp32 NDHWC, l>=1),
+ * gx0 (fp32, may be NULL) and gpoints (B,N,3; may be NULL, needs x0/vols).  Outputs are
+ * accumulated into (caller zero-fills).                                                          */
+int svr_gather_bwd(const float *points, int B, int N, const float *x0, const uint16_t *const *vols_host,
+                   const svr_pyramid *pyr_host, const uint16_t *dfeat, float *gx0, float *const *gvols_host,
+                   float *gpoints, void *stream);
+
+/* tcgen05 GEMMs (Conv1d k=1 of ifnet.py:55-59 and their backward).
+ * NT:  C[M,N] = epi( A[M,K] . B[N,K]^T + bias[N] ),  A,B bf16 row-major, K % 64 == 0.
+ *   flags: bit0 relu, bit1 store bf16 to c_bf16, bit2 store fp32 to c_f32,
+ *          bit3 multiply by (mask[M,N] > 0) (bf16 mask, ld = ldc) -- relu backward,
+ *          bit4 row-dot: out_dot[m] = sum_n epi(..)[m,n]*dot_w[n] + dot_b[0] (fc_out fused; N<=256)
+ * TN:  C[M,N] (+)= A[P,M]^T . B[P,N], A,B bf16 row-major (contraction over rows), fp32 out;
+ *      workspace >= svr_gemm_tn_workspace_bytes(M,N,P).                                          */
+int svr_gemm_nt(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, const float *bias, int M, int N,
+                int K, int flags, uint16_t *c_bf16, float *c_f32, int64_t ldc, const uint16_t *mask,
+                const float *dot_w, const float *dot_b, float *out_dot, void *stream);
+size_t svr_gemm_tn_workspace_bytes(int M, int N, int P);
+int svr_gemm_tn(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, int M, int N, int P, float *C,
+                int64_t ldc, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Small fused helpers of the decoder backward.
+ * dz2[m,n] = dlogit[m] * wout[n] * (h2[m,n] > 0)  (bf16 out); gwout[n] += sum_m dlogit[m]*h2[m,n];
+ * gbout += sum_m dlogit[m].                                                                      */
+int svr_decoder_head_bwd(const float *dlogit, const uint16_t *h2, const float *wout, int M, int Hd,
+                         uint16_t *dz2, float *gwout, float *gbout, void *stream);
+/* column sums of a bf16 (M,N) matrix into fp32 out[N] (bias gradients); accumulate != 0 adds.    */
+int svr_colsum_bf16(const uint16_t *a, int M, int N, int64_t lda, float *out, int accumulate, void *stream);
+
+/* Fused forward: gather -> smem -> tcgen05 fc_0 -> fc_1 -> fc_2 -> fc_out in ONE kernel (128-net,
+ * hidden 256).  logits (B*N) fp32.  If save_h != NULL the three hidden activations (post-ReLU,
+ * bf16, (B*N,256) each, concatenated) and, if save_feat != NULL, the gathered features are kept
+ * for the backward.  Implemented in fused_query.cu.                                              */
+typedef struct svr_decoder_weights {
+    const uint16_t *w0p;   /* (H0, KP) bf16, K' order   */
+    const uint16_t *w1;    /* (H1, H0) bf16             */
+    const uint16_t *w2;    /* (H2, H1) bf16             */
+    const float *b0, *b1, *b2;
+    const float *wout;     /* (H2) fp32                 */
+    const float *bout;     /* (1) fp32, device          */
+    int h0, h1, h2;
+} svr_decoder_weights;
+
+int svr_query_fwd_fused(const float *points, int B, int N, const float *x0, const uint16_t *const *vols_host,
+                        const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, float *logits,
+                        uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream);
+
+/* Dense evaluation (evaluate_network_on_grid, ifnet.py:215-229; make_3d_grid :202-212): evaluates
+ * sigmoid(decoder(sample(x, lattice))) on the (sx,sy,sz) inclusive lattice over [-0.5,0.5]^3 for
+ * z-slab [x_begin, x_end) of the FIRST lattice axis, generating the points on the fly; out is the
+ * (sx,sy,sz) fp32 grid of ONE scene (only the slab is written).                                  */
+int svr_dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host,
+                   const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, int sx, int sy, int sz,
+                   int x_begin, int x_end, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVR_B200_H */

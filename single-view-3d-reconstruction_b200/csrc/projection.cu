@@ -1,0 +1,621 @@
+// Projection path: unproject -> normalise -> bit-exact trilinear voxelisation -> separable blur.
+// Replaces the device work of model/projection.py (reference root) -- see include/svr_b200.h.
+//
+// Voxelisation design (B200-first, not a port of the 8x index_put_):
+//   the dense grid is written once (memset) and only touched voxels are revisited.  Points are
+//   bucketed by their floor cell through a 1-bit-per-cell bitmap + popcount rank (a compact cell
+//   id without sorting 8x the points), counted and placed with INTEGER counters only, ranked by
+//   point index inside each cell, and every touched voxel is then summed by exactly one thread in
+//   the reference's serial order (pass (k,j,i)-major, then point index) with non-contracted fp32
+//   adds.  No floating-point atomics anywhere; results are bit-exact and run-to-run deterministic.
+#include "common.cuh"
+
+namespace svr {
+
+// ------------------------------------------------------------------------------------------------
+// unproject / normalise
+// ------------------------------------------------------------------------------------------------
+struct UnprojParams {
+    float f, cx, cy;
+    float scale[3], offset[3], half[3], size[3];
+    int normalise;
+};
+
+__global__ void unproject_fwd_kernel(const float *__restrict__ depth, int H, int W, int64_t total, UnprojParams p,
+                                     float *__restrict__ pts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int u = (int)(i % W);
+    int v = (int)((i / W) % H);
+    float d = depth[i];
+    float cam[3];
+    cam[0] = __fdiv_rn(__fsub_rn(__fmul_rn((float)u, d), __fmul_rn(p.cx, d)), p.f);
+    cam[1] = -__fdiv_rn(__fsub_rn(__fmul_rn((float)v, d), __fmul_rn(p.cy, d)), p.f);
+    cam[2] = d;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float g = __fadd_rn(__fmul_rn(p.scale[k], cam[k]), p.offset[k]);
+        if (p.normalise) g = __fdiv_rn(__fsub_rn(g, p.half[k]), p.size[k]);
+        pts[i * 3 + k] = g;
+    }
+}
+
+__global__ void unproject_bwd_kernel(const float *__restrict__ gpts, int H, int W, int64_t total, UnprojParams p,
+                                     float *__restrict__ gdepth) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int u = (int)(i % W);
+    int v = (int)((i / W) % H);
+    // cam_k = c_k * d  with c = ((u-cx)/f, -(v-cy)/f, 1);  pts_k = scale_k*cam_k (+const) [/size_k]
+    float c[3] = {((float)u - p.cx) / p.f, -((float)v - p.cy) / p.f, 1.0f};
+    float g = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float s = p.scale[k] * c[k];
+        if (p.normalise) s = s / p.size[k];
+        g += gpts[i * 3 + k] * s;
+    }
+    gdepth[i] = g;
+}
+
+__global__ void norm_grid_space_kernel(float *__restrict__ pts, int64_t n, UnprojParams p) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 3) return;
+    int k = (int)(i % 3);
+    pts[i] = __fdiv_rn(__fsub_rn(pts[i], p.half[k]), p.size[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// voxelisation
+// ------------------------------------------------------------------------------------------------
+struct VoxParams {
+    int B, N;
+    int S[3];
+    int64_t V;       // voxels per map
+    int Wd;          // bitmap words per map
+    float lo, hi;    // validity bounds, fp32(-0.5+eps), fp32(0.5-eps)
+    float Sm1[3];    // fp32(S-1)
+};
+
+// bit-exact per-point quantities (projection.py:44-58); returns validity
+__device__ __forceinline__ bool point_frac(const float *__restrict__ p, const VoxParams &vp, int f[3], float r[3],
+                                           float m[3]) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = p[k];
+        ok = ok && (v < vp.hi) && (v > vp.lo);
+        float g = __fmul_rn(__fadd_rn(v, 0.5f), vp.Sm1[k]);
+        float f0 = floorf(g);
+        f[k] = (int)f0;
+        r[k] = __fsub_rn(g, f0);
+        m[k] = __fsub_rn(1.0f, r[k]);
+    }
+    return ok;
+}
+
+__device__ __forceinline__ float corner_weight(const float r[3], const float m[3], int pass) {
+    float a = (pass & 4) ? r[0] : m[0];
+    float b = (pass & 2) ? r[1] : m[1];
+    float c = (pass & 1) ? r[2] : m[2];
+    return __fmul_rn(__fmul_rn(a, b), c);
+}
+
+// K1: mark occupied cells
+__global__ void vox_mark_kernel(const float *__restrict__ pts, VoxParams vp, int *__restrict__ cell_of_point,
+                                uint32_t *__restrict__ bitmap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)vp.B * vp.N) return;
+    int b = (int)(i / vp.N);
+    int f[3];
+    float r[3], m[3];
+    bool ok = point_frac(pts + i * 3, vp, f, r, m);
+    // the reference would raise on an out-of-range corner; such points cannot pass the validity
+    // test, but guard anyway so a malformed input can never write out of bounds
+    ok = ok && f[0] >= 0 && f[1] >= 0 && f[2] >= 0 && f[0] + 1 < vp.S[0] && f[1] + 1 < vp.S[1] && f[2] + 1 < vp.S[2];
+    int cell = -1;
+    if (ok) {
+        cell = (f[0] * vp.S[1] + f[1]) * vp.S[2] + f[2];
+        atomicOr(bitmap + (size_t)b * vp.Wd + (cell >> 5), 1u << (cell & 31));
+    }
+    cell_of_point[i] = cell;
+}
+
+// exclusive scan of one map's array by one CTA (1024 threads); MODE 0: popcount of words, 1: ints
+template <int MODE>
+__global__ void __launch_bounds__(1024) scan_per_map_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                            int n_static, const int *__restrict__ n_dynamic,
+                                                            int stride, int *__restrict__ total_out) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s, chunk_total_s;
+    const int b = blockIdx.x;
+    const int n = n_dynamic ? n_dynamic[b] : n_static;
+    const uint32_t *src = in + (size_t)b * stride;
+    uint32_t *dst = out + (size_t)b * stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < n) v = MODE == 0 ? (uint32_t)__popc(src[i]) : src[i];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;  // exclusive prefix of the warp totals
+            if (lane == 31) chunk_total_s = wi;
+        }
+        __syncthreads();
+        uint32_t excl = carry_s + warp_sums[warp] + incl - v;
+        if (i < n) dst[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_total_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) total_out[b] = (int)carry_s;
+}
+
+__device__ __forceinline__ int cell_rank(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wprefix,
+                                         int cell) {
+    uint32_t w = bitmap[cell >> 5];
+    return (int)(wprefix[cell >> 5] + __popc(w & ((1u << (cell & 31)) - 1u)));
+}
+
+// K3: compact id per point, per-cell counts, linear index per compact id
+__global__ void vox_count_kernel(VoxParams vp, const int *__restrict__ cell_of_point, const uint32_t *__restrict__ bitmap,
+                                 const uint32_t *__restrict__ wprefix, int *__restrict__ cid_of_point,
+                                 int *__restrict__ count, int *__restrict__ cell_lin) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)vp.B * vp.N) return;
+    int b = (int)(i / vp.N);
+    int cell = cell_of_point[i];
+    int id = -1;
+    if (cell >= 0) {
+        id = cell_rank(bitmap + (size_t)b * vp.Wd, wprefix + (size_t)b * vp.Wd, cell);
+        atomicAdd(count + (size_t)b * vp.N + id, 1);
+        cell_lin[(size_t)b * vp.N + id] = cell;  // every writer stores the same value
+    }
+    cid_of_point[i] = id;
+}
+
+// K5: place points into their cell's run (arbitrary order inside the run, fixed by K6)
+__global__ void vox_fill_kernel(VoxParams vp, const int *__restrict__ cid_of_point, const int *__restrict__ start,
+                                int *__restrict__ cursor, int *__restrict__ order) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)vp.B * vp.N) return;
+    int b = (int)(i / vp.N), n = (int)(i % vp.N);
+    int id = cid_of_point[i];
+    if (id < 0) return;
+    size_t o = (size_t)b * vp.N;
+    int slot = start[o + id] + atomicAdd(cursor + o + id, 1);
+    order[o + slot] = n;
+}
+
+// K6: rank every point inside its cell by point index (counting smaller indices) -> deterministic
+__global__ void vox_rank_kernel(VoxParams vp, const int *__restrict__ cid_of_point, const int *__restrict__ start,
+                                const int *__restrict__ count, const int *__restrict__ order,
+                                int *__restrict__ sorted) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)vp.B * vp.N) return;
+    int b = (int)(i / vp.N), n = (int)(i % vp.N);
+    int id = cid_of_point[i];
+    if (id < 0) return;
+    size_t o = (size_t)b * vp.N;
+    int s = start[o + id], c = count[o + id];
+    int rank = 0;
+    for (int t = 0; t < c; ++t) rank += (order[o + s + t] < n);
+    sorted[o + s + rank] = n;
+}
+
+// K7: one thread per (occupied cell, corner shift) candidate; the owner of the target voxel sums
+// all contributions in reference order and writes the voxel.
+__global__ void vox_accumulate_kernel(const float *__restrict__ pts, VoxParams vp, const int *__restrict__ ucount,
+                                      const int *__restrict__ cell_lin, const uint32_t *__restrict__ bitmap,
+                                      const uint32_t *__restrict__ wprefix, const int *__restrict__ start,
+                                      const int *__restrict__ count, const int *__restrict__ sorted,
+                                      int64_t tail_start, float *__restrict__ grid, uint32_t *__restrict__ sat_mask) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)vp.B * vp.N * 8) return;
+    int shift = (int)(t & 7);
+    int64_t cu = t >> 3;
+    int b = (int)(cu / vp.N), u = (int)(cu % vp.N);
+    if (u >= ucount[b]) return;
+    const size_t o = (size_t)b * vp.N;
+    const uint32_t *bm = bitmap + (size_t)b * vp.Wd;
+    const uint32_t *wp = wprefix + (size_t)b * vp.Wd;
+    int cell = cell_lin[o + u];
+    int cz = cell / (vp.S[1] * vp.S[2]);
+    int cy = (cell / vp.S[2]) % vp.S[1];
+    int cx = cell % vp.S[2];
+    int vz = cz + ((shift >> 2) & 1), vy = cy + ((shift >> 1) & 1), vx = cx + (shift & 1);
+    // source cell of every pass for this voxel, and ownership: the first pass with an occupied cell
+    int src_id[8];
+    bool owner = true;
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+        int sz = vz - ((ps >> 2) & 1), sy = vy - ((ps >> 1) & 1), sx = vx - (ps & 1);
+        int id = -1;
+        if (sz >= 0 && sy >= 0 && sx >= 0 && sz < vp.S[0] && sy < vp.S[1] && sx < vp.S[2]) {
+            int c = (sz * vp.S[1] + sy) * vp.S[2] + sx;
+            if ((bm[c >> 5] >> (c & 31)) & 1u) id = cell_rank(bm, wp, c);
+        }
+        src_id[ps] = id;
+        if (ps < shift && id >= 0) owner = false;
+    }
+    if (!owner) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+        int id = src_id[ps];
+        if (id < 0) continue;
+        int s = start[o + id], c = count[o + id];
+        for (int q = 0; q < c; ++q) {
+            int n = sorted[o + s + q];
+            int f[3];
+            float r[3], m[3];
+            point_frac(pts + (o + n) * 3, vp, f, r, m);
+            acc = __fadd_rn(acc, corner_weight(r, m, ps));
+        }
+    }
+    int64_t flat = (int64_t)b * vp.V + ((int64_t)vz * vp.S[1] + vy) * vp.S[2] + vx;
+    float s8;
+    if (flat < tail_start) {  // torch.stack(8 aliases).sum(0): row-after-row accumulation
+        s8 = acc;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) s8 = __fadd_rn(s8, acc);
+    } else {                  // ATen row_sum remainder path: 4 interleaved partial sums
+        float p2 = __fadd_rn(acc, acc);
+        s8 = __fadd_rn(__fadd_rn(__fadd_rn(p2, p2), p2), p2);
+    }
+    if (sat_mask && s8 > 1.0f) atomicOr(sat_mask + (flat >> 5), 1u << (flat & 31));
+    grid[flat] = s8 < 0.f ? 0.f : (s8 > 1.f ? 1.f : s8);
+}
+
+__global__ void vox_bwd_kernel(const float *__restrict__ pts, const float *__restrict__ ggrid,
+                               const uint32_t *__restrict__ sat_mask, VoxParams vp, float *__restrict__ gpts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)vp.B * vp.N) return;
+    int b = (int)(i / vp.N);
+    int f[3];
+    float r[3], m[3];
+    bool ok = point_frac(pts + i * 3, vp, f, r, m);
+    ok = ok && f[0] >= 0 && f[1] >= 0 && f[2] >= 0 && f[0] + 1 < vp.S[0] && f[1] + 1 < vp.S[1] && f[2] + 1 < vp.S[2];
+    float g[3] = {0.f, 0.f, 0.f};
+    if (ok) {
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+            int k = (ps >> 2) & 1, j = (ps >> 1) & 1, ii = ps & 1;
+            int64_t flat = (int64_t)b * vp.V + ((int64_t)(f[0] + k) * vp.S[1] + (f[1] + j)) * vp.S[2] + (f[2] + ii);
+            bool sat = sat_mask ? ((sat_mask[flat >> 5] >> (flat & 31)) & 1u) : false;
+            float G = sat ? 0.f : 8.0f * ggrid[flat];
+            float w0 = k ? r[0] : m[0], w1 = j ? r[1] : m[1], w2 = ii ? r[2] : m[2];
+            g[0] += G * (k ? 1.f : -1.f) * w1 * w2;
+            g[1] += G * (j ? 1.f : -1.f) * w0 * w2;
+            g[2] += G * (ii ? 1.f : -1.f) * w0 * w1;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gpts[i * 3 + k] = g[k] * vp.Sm1[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// separable blur
+// ------------------------------------------------------------------------------------------------
+// out[pos] = sum_t taps[t] * in[pos + (t - r) along axis] (zero outside), optional clamp(0,1)
+__global__ void conv_axis_kernel(const float *__restrict__ in, float *__restrict__ out, int D, int H, int W,
+                                 int64_t total, int axis, const float *__restrict__ taps, int k, int flip, int clamp01) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int x = (int)(i % W), y = (int)((i / W) % H), z = (int)((i / ((int64_t)W * H)) % D);
+    int pos = axis == 0 ? z : (axis == 1 ? y : x);
+    int len = axis == 0 ? D : (axis == 1 ? H : W);
+    int64_t stride = axis == 0 ? (int64_t)H * W : (axis == 1 ? W : 1);
+    int r = k / 2;
+    float acc = 0.f;
+    for (int t = 0; t < k; ++t) {
+        int q = pos + t - r;
+        if (q >= 0 && q < len) acc += __ldg(taps + (flip ? k - 1 - t : t)) * in[i + (int64_t)(t - r) * stride];
+    }
+    if (clamp01) acc = fminf(fmaxf(acc, 0.f), 1.f);
+    out[i] = acc;
+}
+
+// g3 = gout * [conv_d(t1) <= 1]   (clamp backward with inclusive bounds; values are never < 0)
+__global__ void clamp_mask_kernel(const float *__restrict__ t1, const float *__restrict__ gout, float *__restrict__ g3,
+                                  int D, int H, int W, int64_t total, const float *__restrict__ taps, int k) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int z = (int)((i / ((int64_t)W * H)) % D);
+    int64_t stride = (int64_t)H * W;
+    int r = k / 2;
+    float acc = 0.f;
+    for (int t = 0; t < k; ++t) {
+        int q = z + t - r;
+        if (q >= 0 && q < D) acc += __ldg(taps + t) * t1[i + (int64_t)(t - r) * stride];
+    }
+    g3[i] = (acc >= 0.f && acc <= 1.f) ? gout[i] : 0.f;
+}
+
+// partial[block][t] = sum over the block's positions of g[pos] * src[pos + (t-r) along axis]
+__global__ void __launch_bounds__(256) tap_grad_kernel(const float *__restrict__ g, const float *__restrict__ src,
+                                                       int D, int H, int W, int64_t total, int axis, int k,
+                                                       float *__restrict__ partial) {
+    __shared__ float red[8][SVR_MAX_TAPS];
+    float loc[SVR_MAX_TAPS];
+#pragma unroll
+    for (int t = 0; t < SVR_MAX_TAPS; ++t) loc[t] = 0.f;
+    int r = k / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % W), y = (int)((i / W) % H), z = (int)((i / ((int64_t)W * H)) % D);
+        int pos = axis == 0 ? z : (axis == 1 ? y : x);
+        int len = axis == 0 ? D : (axis == 1 ? H : W);
+        int64_t stride = axis == 0 ? (int64_t)H * W : (axis == 1 ? W : 1);
+        float gv = g[i];
+        if (gv != 0.f) {
+#pragma unroll
+            for (int t = 0; t < SVR_MAX_TAPS; ++t) {
+                if (t < k) {
+                    int q = pos + t - r;
+                    if (q >= 0 && q < len) loc[t] += gv * src[i + (int64_t)(t - r) * stride];
+                }
+            }
+        }
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < SVR_MAX_TAPS; ++t) {
+        float v = loc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < k) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * SVR_MAX_TAPS + threadIdx.x] = v;
+    }
+}
+
+__global__ void tap_grad_reduce_kernel(const float *__restrict__ partial, int nblocks, int k, float *__restrict__ out) {
+    // one warp per tap, fixed summation order -> deterministic
+    int t = blockIdx.x;
+    if (t >= k) return;
+    float v = 0.f;
+    for (int b = threadIdx.x; b < nblocks; b += 32) v += partial[(size_t)b * SVR_MAX_TAPS + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[t] = v;
+}
+
+static int fill_unproj(UnprojParams &p, float f, float cx, float cy, const float *scale3, const float *offset3,
+                       const int64_t *dims3, int normalise) {
+    p.f = f;
+    p.cx = cx;
+    p.cy = cy;
+    for (int k = 0; k < 3; ++k) {
+        p.scale[k] = scale3 ? scale3[k] : 1.f;
+        p.offset[k] = offset3 ? offset3[k] : 0.f;
+        p.half[k] = dims3 ? (float)((double)dims3[k] / 2.0) : 0.f;
+        p.size[k] = dims3 ? (float)dims3[k] : 1.f;
+    }
+    p.normalise = normalise;
+    return 0;
+}
+
+static int fill_vox(VoxParams &vp, int B, int N, const int64_t *dims3, double eps) {
+    SVR_REQUIRE(B >= 0 && N >= 0, "voxelize: negative sizes");
+    SVR_REQUIRE(dims3 && dims3[0] >= 2 && dims3[1] >= 2 && dims3[2] >= 2, "voxelize: every grid axis must be >= 2");
+    int64_t V = dims3[0] * dims3[1] * dims3[2];
+    SVR_REQUIRE(V < (int64_t)1 << 31, "voxelize: more than 2^31 voxels per map");
+    SVR_REQUIRE((int64_t)B * N * 8 < ((int64_t)1 << 40), "voxelize: too many points");
+    vp.B = B;
+    vp.N = N;
+    vp.V = V;
+    vp.Wd = (int)((V + 31) / 32);
+    for (int k = 0; k < 3; ++k) {
+        vp.S[k] = (int)dims3[k];
+        vp.Sm1[k] = (float)(dims3[k] - 1);
+    }
+    vp.hi = (float)(0.5 - eps);    // python double arithmetic, then cast to the tensor dtype
+    vp.lo = (float)(-0.5 + eps);
+    return 0;
+}
+
+struct VoxWorkspace {
+    int *cell_of_point, *cid_of_point, *cell_lin, *count, *start, *cursor, *order, *sorted, *ucount;
+    uint32_t *bitmap, *wprefix;
+    size_t bytes, zero_bytes;   // [bitmap | count | cursor] are contiguous and zero-filled per call
+};
+
+static void layout_ws(VoxWorkspace &w, char *base, int B, int N, int Wd) {
+    size_t bn = (size_t)B * N, bw = (size_t)B * Wd;
+    auto take = [&](size_t n_elems) {
+        char *p = base;
+        base += ((n_elems * 4 + 255) / 256) * 256;
+        return p;
+    };
+    char *origin = base;
+    w.bitmap = (uint32_t *)take(bw);
+    w.count = (int *)take(bn);
+    w.cursor = (int *)take(bn);
+    w.zero_bytes = (size_t)(base - origin);
+    w.wprefix = (uint32_t *)take(bw);
+    w.cell_of_point = (int *)take(bn);
+    w.cid_of_point = (int *)take(bn);
+    w.cell_lin = (int *)take(bn);
+    w.start = (int *)take(bn);
+    w.order = (int *)take(bn);
+    w.sorted = (int *)take(bn);
+    w.ucount = (int *)take((size_t)B);
+    w.bytes = (size_t)(base - origin);
+}
+
+}  // namespace svr
+
+using namespace svr;
+
+extern "C" {
+
+int svr_unproject_fwd(const float *depth, int B, int H, int W, float f, float cx, float cy, const float *scale3_host,
+                      const float *offset3_host, const int64_t *dims3_host, int normalise, float *pts, void *stream) {
+    SVR_REQUIRE(depth && pts && scale3_host && offset3_host, "unproject: null pointer");
+    SVR_REQUIRE(!normalise || dims3_host, "unproject: dims required when normalise is set");
+    UnprojParams p;
+    fill_unproj(p, f, cx, cy, scale3_host, offset3_host, dims3_host, normalise);
+    int64_t total = (int64_t)B * H * W;
+    if (total == 0) return 0;
+    unproject_fwd_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(depth, H, W, total, p, pts);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_unproject_bwd(const float *grad_pts, int B, int H, int W, float f, float cx, float cy,
+                      const float *scale3_host, const int64_t *dims3_host, int normalise, float *grad_depth,
+                      void *stream) {
+    SVR_REQUIRE(grad_pts && grad_depth && scale3_host, "unproject_bwd: null pointer");
+    UnprojParams p;
+    fill_unproj(p, f, cx, cy, scale3_host, nullptr, dims3_host, normalise);
+    int64_t total = (int64_t)B * H * W;
+    if (total == 0) return 0;
+    unproject_bwd_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(grad_pts, H, W, total, p,
+                                                                                               grad_depth);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_norm_grid_space(float *pts, int64_t n_points, const int64_t *dims3_host, void *stream) {
+    SVR_REQUIRE(pts && dims3_host, "norm_grid_space: null pointer");
+    UnprojParams p;
+    fill_unproj(p, 1.f, 0.f, 0.f, nullptr, nullptr, dims3_host, 1);
+    if (n_points == 0) return 0;
+    norm_grid_space_kernel<<<(unsigned)ceil_div<int64_t>(n_points * 3, 256), 256, 0, as_stream(stream)>>>(pts, n_points, p);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t svr_voxelize_workspace_bytes(int B, int N, const int64_t *dims3_host) {
+    if (!dims3_host || B <= 0 || N <= 0) return 256;
+    int64_t V = dims3_host[0] * dims3_host[1] * dims3_host[2];
+    VoxWorkspace w;
+    layout_ws(w, nullptr, B, N, (int)((V + 31) / 32));
+    return w.bytes + 256;
+}
+
+int svr_voxelize_fwd(const float *pts, int B, int N, const int64_t *dims3_host, double eps, int64_t tail_start,
+                     float *grid, uint32_t *sat_mask, void *workspace, size_t workspace_bytes, void *stream) {
+    VoxParams vp;
+    if (int rc = fill_vox(vp, B, N, dims3_host, eps)) return rc;
+    SVR_REQUIRE(grid, "voxelize: null grid");
+    cudaStream_t st = as_stream(stream);
+    int64_t total_vox = (int64_t)B * vp.V;
+    if (tail_start < 0 || tail_start > total_vox) tail_start = total_vox;
+    if (total_vox == 0) return 0;
+    SVR_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), st));
+    if (sat_mask) SVR_CUDA(cudaMemsetAsync(sat_mask, 0, (size_t)((total_vox + 31) / 32) * 4, st));
+    if (N == 0) return 0;
+    SVR_REQUIRE(pts && workspace, "voxelize: null pointer");
+    SVR_REQUIRE(((uintptr_t)workspace & 255) == 0, "voxelize: workspace must be 256-byte aligned");
+    VoxWorkspace w;
+    layout_ws(w, (char *)workspace, B, N, vp.Wd);
+    SVR_REQUIRE(workspace_bytes >= w.bytes, "voxelize: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    SVR_CUDA(cudaMemsetAsync(w.bitmap, 0, w.zero_bytes, st));
+    const int64_t bn = (int64_t)B * N;
+    const unsigned gp = (unsigned)ceil_div<int64_t>(bn, 256);
+    vox_mark_kernel<<<gp, 256, 0, st>>>(pts, vp, w.cell_of_point, w.bitmap);
+    SVR_LAUNCH_CHECK();
+    scan_per_map_kernel<0><<<B, 1024, 0, st>>>(w.bitmap, w.wprefix, vp.Wd, nullptr, vp.Wd, w.ucount);
+    SVR_LAUNCH_CHECK();
+    vox_count_kernel<<<gp, 256, 0, st>>>(vp, w.cell_of_point, w.bitmap, w.wprefix, w.cid_of_point, w.count, w.cell_lin);
+    SVR_LAUNCH_CHECK();
+    scan_per_map_kernel<1><<<B, 1024, 0, st>>>((const uint32_t *)w.count, (uint32_t *)w.start, N, w.ucount, N, nullptr);
+    SVR_LAUNCH_CHECK();
+    vox_fill_kernel<<<gp, 256, 0, st>>>(vp, w.cid_of_point, w.start, w.cursor, w.order);
+    SVR_LAUNCH_CHECK();
+    vox_rank_kernel<<<gp, 256, 0, st>>>(vp, w.cid_of_point, w.start, w.count, w.order, w.sorted);
+    SVR_LAUNCH_CHECK();
+    vox_accumulate_kernel<<<(unsigned)ceil_div<int64_t>(bn * 8, 256), 256, 0, st>>>(
+        pts, vp, w.ucount, w.cell_lin, w.bitmap, w.wprefix, w.start, w.count, w.sorted, tail_start, grid, sat_mask);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_voxelize_bwd(const float *pts, const float *grad_grid, const uint32_t *sat_mask, int B, int N,
+                     const int64_t *dims3_host, double eps, float *grad_pts, void *stream) {
+    VoxParams vp;
+    if (int rc = fill_vox(vp, B, N, dims3_host, eps)) return rc;
+    if ((int64_t)B * N == 0) return 0;
+    SVR_REQUIRE(pts && grad_grid && grad_pts, "voxelize_bwd: null pointer");
+    vox_bwd_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)B * N, 256), 256, 0, as_stream(stream)>>>(pts, grad_grid, sat_mask,
+                                                                                                 vp, grad_pts);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+static int check_taps(const float *t, int k) {
+    SVR_REQUIRE(t && k >= 1 && k <= SVR_MAX_TAPS && (k & 1), "blur: tap count must be odd and <= %d (got %d)", SVR_MAX_TAPS, k);
+    return 0;
+}
+
+int svr_blur_fwd(const float *in, int B, int D, int H, int W, const float *taps_w, int kw, const float *taps_h, int kh,
+                 const float *taps_d, int kd, float *out, float *tmp0, float *tmp1, void *stream) {
+    SVR_REQUIRE(in && out && tmp0 && tmp1, "blur: null pointer");
+    if (int rc = check_taps(taps_w, kw)) return rc;
+    if (int rc = check_taps(taps_h, kh)) return rc;
+    if (int rc = check_taps(taps_d, kd)) return rc;
+    int64_t total = (int64_t)B * D * H * W;
+    if (total == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    unsigned g = (unsigned)ceil_div<int64_t>(total, 256);
+    conv_axis_kernel<<<g, 256, 0, st>>>(in, tmp0, D, H, W, total, 2, taps_w, kw, 0, 0);
+    conv_axis_kernel<<<g, 256, 0, st>>>(tmp0, tmp1, D, H, W, total, 1, taps_h, kh, 0, 0);
+    conv_axis_kernel<<<g, 256, 0, st>>>(tmp1, out, D, H, W, total, 0, taps_d, kd, 0, 1);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_blur_bwd(const float *in, const float *grad_out, int B, int D, int H, int W, const float *taps_w, int kw,
+                 const float *taps_h, int kh, const float *taps_d, int kd, float *grad_in, float *grad_taps, float *tmp,
+                 void *stream) {
+    SVR_REQUIRE(in && grad_out && grad_in && grad_taps && tmp, "blur_bwd: null pointer");
+    if (int rc = check_taps(taps_w, kw)) return rc;
+    if (int rc = check_taps(taps_h, kh)) return rc;
+    if (int rc = check_taps(taps_d, kd)) return rc;
+    int64_t total = (int64_t)B * D * H * W;
+    if (total == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    unsigned g = (unsigned)ceil_div<int64_t>(total, 256);
+    float *T0 = tmp, *T1 = tmp + total, *T2 = tmp + 2 * total, *T3 = tmp + 3 * total;
+    // the tap-gradient partial sums use the head of grad_in (written last) as scratch
+    int nblocks = (int)((total / 256 < 1184) ? (total / 256 > 0 ? total / 256 : 1) : 1184);
+    SVR_REQUIRE((int64_t)nblocks * SVR_MAX_TAPS <= total, "blur_bwd: grid too small for the tap-gradient scratch");
+    float *partial = grad_in;
+    conv_axis_kernel<<<g, 256, 0, st>>>(in, T0, D, H, W, total, 2, taps_w, kw, 0, 0);        // t0 = conv_w(x)
+    conv_axis_kernel<<<g, 256, 0, st>>>(T0, T1, D, H, W, total, 1, taps_h, kh, 0, 0);        // t1 = conv_h(t0)
+    clamp_mask_kernel<<<g, 256, 0, st>>>(T1, grad_out, T2, D, H, W, total, taps_d, kd);      // g3
+    tap_grad_kernel<<<nblocks, 256, 0, st>>>(T2, T1, D, H, W, total, 0, kd, partial);
+    tap_grad_reduce_kernel<<<kd, 32, 0, st>>>(partial, nblocks, kd, grad_taps + kw + kh);
+    conv_axis_kernel<<<g, 256, 0, st>>>(T2, T3, D, H, W, total, 0, taps_d, kd, 1, 0);        // g2
+    tap_grad_kernel<<<nblocks, 256, 0, st>>>(T3, T0, D, H, W, total, 1, kh, partial);
+    tap_grad_reduce_kernel<<<kh, 32, 0, st>>>(partial, nblocks, kh, grad_taps + kw);
+    conv_axis_kernel<<<g, 256, 0, st>>>(T3, T2, D, H, W, total, 1, taps_h, kh, 1, 0);        // g1
+    tap_grad_kernel<<<nblocks, 256, 0, st>>>(T2, in, D, H, W, total, 2, kw, partial);
+    tap_grad_reduce_kernel<<<kw, 32, 0, st>>>(partial, nblocks, kw, grad_taps);
+    conv_axis_kernel<<<g, 256, 0, st>>>(T2, grad_in, D, H, W, total, 2, taps_w, kw, 1, 0);   // grad_in
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+}

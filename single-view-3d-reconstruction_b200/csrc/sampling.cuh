@@ -1,0 +1,192 @@
+// Device-side description of the sampled feature pyramid and the trilinear stencil math shared by
+// the gather / scatter kernels and the fused query kernel.
+//
+// Feature axis layout ("K' order").  The reference concatenates levels on channels and flattens
+// (C,7) -> k = c*7 + d (model/ifnet.py:43-45,197).  The kernels use 16-byte UNITS of 8 bf16
+// channels so that one unit == one contiguous channel-last load per corner:
+//   unit 0            : level 0 (1 channel): the 7 stencil samples d=0..6, then one zero
+//   units of level l  : for d in 0..6, for g in 0..C_l/8-1 : channels g*8..g*8+7 of stencil point d
+//   padding units     : zeros up to KP = 64 * ceil(units/8)
+// fc_0's weight is permuted to the same order once per weight update (svr_pack_w0).
+#pragma once
+#include "common.cuh"
+
+namespace svr {
+
+struct Pyr {
+    int n_levels;
+    int C[SVR_MAX_LEVELS], D[SVR_MAX_LEVELS], H[SVR_MAX_LEVELS], W[SVR_MAX_LEVELS];
+    int upd[SVR_MAX_LEVELS];        // units per stencil point (C/8), level >= 1
+    int ubase[SVR_MAX_LEVELS + 1];  // first unit of each level; ubase[n_levels] = number of real units
+    int coff[SVR_MAX_LEVELS];       // channel offset in the reference's concat order
+    int n_units, kp, ctot;
+    int align;
+    float delta;
+};
+
+// host: validate + derive
+static inline int make_pyr(Pyr &P, const svr_pyramid *h) {
+    SVR_REQUIRE(h, "pyramid: null");
+    SVR_REQUIRE(h->n_levels >= 2 && h->n_levels <= SVR_MAX_LEVELS, "pyramid: n_levels must be in [2,%d]", SVR_MAX_LEVELS);
+    SVR_REQUIRE(h->channels[0] == 1, "pyramid: level 0 must have exactly one channel");
+    P.n_levels = h->n_levels;
+    int u = 1, c = 0;
+    for (int l = 0; l < h->n_levels; ++l) {
+        SVR_REQUIRE(h->dims[l][0] > 0 && h->dims[l][1] > 0 && h->dims[l][2] > 0, "pyramid: empty level %d", l);
+        SVR_REQUIRE(l == 0 || (h->channels[l] > 0 && h->channels[l] % 8 == 0), "pyramid: level %d channels must be a multiple of 8", l);
+        P.C[l] = h->channels[l];
+        P.D[l] = h->dims[l][0];
+        P.H[l] = h->dims[l][1];
+        P.W[l] = h->dims[l][2];
+        P.coff[l] = c;
+        c += h->channels[l];
+        if (l == 0) {
+            P.upd[0] = 1;
+            P.ubase[0] = 0;
+        } else {
+            P.upd[l] = h->channels[l] / 8;
+            P.ubase[l] = u;
+            u += 7 * P.upd[l];
+        }
+    }
+    for (int l = h->n_levels; l <= SVR_MAX_LEVELS; ++l) P.ubase[l] = u;
+    for (int l = h->n_levels; l < SVR_MAX_LEVELS; ++l) P.C[l] = P.D[l] = P.H[l] = P.W[l] = P.upd[l] = P.coff[l] = 0;
+    P.n_units = u;
+    P.kp = ((u + 7) / 8) * 64;
+    P.ctot = c;
+    P.align = h->align_corners ? 1 : 0;
+    P.delta = h->displacement;
+    return 0;
+}
+
+#ifdef __CUDACC__
+// unit -> (level, stencil index, first channel); returns false for padding units
+__device__ __forceinline__ bool decode_unit(const Pyr &P, int u, int &level, int &d, int &c0) {
+    if (u >= P.n_units) return false;
+    level = 0;
+#pragma unroll
+    for (int l = 1; l < SVR_MAX_LEVELS; ++l)
+        if (l < P.n_levels && u >= P.ubase[l]) level = l;
+    int t = u - P.ubase[level];
+    d = t / P.upd[level];
+    c0 = (t - d * P.upd[level]) * 8;
+    return true;
+}
+
+// 8 trilinear corners of one stencil sample in one level
+struct Corners {
+    int x0, y0, z0;
+    float wx[2], wy[2], wz[2];
+};
+
+// model/ifnet.py:156-159 + F.grid_sample unnormalisation (ATen GridSampler.h:27-35)
+__device__ __forceinline__ void stencil_corners(const Pyr &P, int level, int d, float px, float py, float pz, Corners &c) {
+    // point coords are (D,H,W)-ordered; grid_sample's x indexes W, y indexes H, z indexes D
+    float q[3] = {__fmul_rn(2.0f, pz), __fmul_rn(2.0f, py), __fmul_rn(2.0f, px)};
+    if (d > 0) {
+        int axis = (d - 1) >> 1;
+        float s = ((d - 1) & 1) ? P.delta : -P.delta;
+        q[axis] = __fadd_rn(q[axis], s);
+    }
+    const int size[3] = {P.W[level], P.H[level], P.D[level]};
+    float idx[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float sz = (float)size[a];
+        idx[a] = P.align ? __fmul_rn(__fmul_rn(__fadd_rn(q[a], 1.0f), 0.5f), sz - 1.0f)
+                         : __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(q[a], 1.0f), sz), 1.0f), 0.5f);
+    }
+    float fx = floorf(idx[0]), fy = floorf(idx[1]), fz = floorf(idx[2]);
+    // clamp the integer base so that wildly out-of-range points cannot overflow int arithmetic;
+    // every corner of such a sample is out of bounds and contributes zero either way
+    fx = fminf(fmaxf(fx, -4.0f), (float)size[0] + 2.0f);
+    fy = fminf(fmaxf(fy, -4.0f), (float)size[1] + 2.0f);
+    fz = fminf(fmaxf(fz, -4.0f), (float)size[2] + 2.0f);
+    c.x0 = (int)fx;
+    c.y0 = (int)fy;
+    c.z0 = (int)fz;
+    c.wx[1] = idx[0] - fx;
+    c.wx[0] = (fx + 1.0f) - idx[0];
+    c.wy[1] = idx[1] - fy;
+    c.wy[0] = (fy + 1.0f) - idx[1];
+    c.wz[1] = idx[2] - fz;
+    c.wz[0] = (fz + 1.0f) - idx[2];
+}
+
+__device__ __forceinline__ bool corner_in(const Pyr &P, int level, int x, int y, int z) {
+    return x >= 0 && y >= 0 && z >= 0 && x < P.W[level] && y < P.H[level] && z < P.D[level];
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4 &raw, float (&f)[8]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__device__ __forceinline__ uint4 float8_to_bf16(const float (&f)[8]) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return *reinterpret_cast<uint4 *>(h);
+}
+
+// One unit of the feature row of a point: 8 bf16 values packed in a uint4.
+//   x0_b  : level-0 grid of the point's scene (fp32, D*H*W)
+//   vol_b : per-level bf16 NDHWC volume base of the point's scene (index 0 unused)
+__device__ __forceinline__ uint4 gather_unit(const Pyr &P, int u, float px, float py, float pz, const float *__restrict__ x0_b,
+                                             const __nv_bfloat16 *const *vol_b) {
+    int level, d, c0;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (!decode_unit(P, u, level, d, c0)) return make_uint4(0, 0, 0, 0);
+    if (level == 0) {
+#pragma unroll
+        for (int dd = 0; dd < 7; ++dd) {
+            Corners c;
+            stencil_corners(P, 0, dd, px, py, pz, c);
+            float a = 0.f;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int aa = 0; aa < 2; ++aa) {
+                        int x = c.x0 + aa, y = c.y0 + b, z = c.z0 + e;
+                        if (corner_in(P, 0, x, y, z))
+                            a += __ldg(x0_b + ((int64_t)z * P.H[0] + y) * P.W[0] + x) * (c.wx[aa] * c.wy[b] * c.wz[e]);
+                    }
+            acc[dd] = a;
+        }
+        return float8_to_bf16(acc);
+    }
+    Corners c;
+    stencil_corners(P, level, d, px, py, pz, c);
+    const __nv_bfloat16 *vb = vol_b[level] + c0;
+    const int C = P.C[level];
+    uint4 raw[8];
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int aa = k & 1, b = (k >> 1) & 1, e = k >> 2;
+        int x = c.x0 + aa, y = c.y0 + b, z = c.z0 + e;
+        bool in = corner_in(P, level, x, y, z);
+        w[k] = in ? c.wx[aa] * c.wy[b] * c.wz[e] : 0.f;
+        raw[k] = in ? __ldg(reinterpret_cast<const uint4 *>(vb + (((int64_t)z * P.H[level] + y) * P.W[level] + x) * C))
+                    : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float f[8];
+        bf16x8_to_float(raw[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[k], acc[j]);
+    }
+    return float8_to_bf16(acc);
+}
+#endif  // __CUDACC__
+
+}  // namespace svr

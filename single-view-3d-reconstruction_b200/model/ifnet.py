@@ -1,0 +1,235 @@
+"""B200-native drop-in for the reference's ``model/ifnet.py``.
+
+Same public names, signatures and state_dict keys (``fc_0 .. fc_out``, ``ifnet_feature_extractor.*``)
+as the reference.  The Conv3d/BatchNorm/MaxPool encoder stays on torch/cuDNN (BASELINE.json
+north_star); everything after it -- the 7-point-stencil trilinear sampling of all feature volumes
+and the pointwise MLP decoder, forward and backward -- runs in the kernels of csrc/ through the
+C ABI.  Citations (file:line) refer to the reference root."""
+from __future__ import annotations
+
+import types
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def _load_args():
+    """The reference parses sys.argv at import (ifnet.py:8).  When its ``util.arguments`` is
+    importable and the command line parses, use it; otherwise fall back to its defaults
+    (util/arguments.py:20,27-29)."""
+    try:
+        from util import arguments as _ref_arguments  # type: ignore
+        if hasattr(_ref_arguments, "parse_arguments"):
+            return _ref_arguments.parse_arguments()
+    except (ImportError, SystemExit, Exception):
+        pass
+    return types.SimpleNamespace(net_res=128, inf_res=1, num_points=2048, batch_size=16)
+
+
+args = _load_args()
+
+
+def configure(**kw):
+    """Override module-level settings (net_res, inf_res, num_points, batch_size)."""
+    for k, v in kw.items():
+        setattr(args, k, v)
+
+
+def _displacements(delta: float) -> torch.Tensor:
+    rows = [[0, 0, 0]]
+    for axis in range(3):
+        for sgn in (-1, 1):
+            r = [0, 0, 0]
+            r[axis] = sgn * delta
+            rows.append(r)
+    return torch.Tensor(rows)
+
+
+class _ExtractorBase(nn.Module):
+    """Shared machinery of the two encoders: ``encode`` returns the sampled volumes, ``forward``
+    reproduces the reference's (B, C, 1, 7, N) feature tensor through the gather kernel."""
+
+    displacement: float
+    align_corners: bool
+
+    def encode(self, x) -> List[torch.Tensor]:
+        raise NotImplementedError
+
+    def pyramid(self, x, vols) -> ops.PyramidSpec:
+        chans = [1] + [v.shape[1] for v in vols]
+        dims = [x.shape[2:]] + [v.shape[2:] for v in vols]
+        key = (tuple(chans), tuple(tuple(d) for d in dims))
+        cache = self.__dict__.setdefault("_pyr_cache", {})
+        if key not in cache:
+            cache[key] = ops.PyramidSpec(chans, dims, self.align_corners, self.displacement)
+        return cache[key]
+
+    def forward(self, x, points):
+        vols = self.encode(x)
+        pyr = self.pyramid(x, vols)
+        feat = ops.gather(pyr, points, x, vols)                       # (B*N, KP) bf16, kernel order
+        idx = self.__dict__.setdefault("_idx_cache", {})
+        if (pyr.channels, feat.device) not in idx:
+            idx[(pyr.channels, feat.device)] = ops.feature_index_map(pyr, feat.device)
+        B, N = points.shape[0], points.shape[1]
+        ref = feat.float().index_select(1, idx[(pyr.channels, feat.device)])   # (B*N, C*7), k = c*7+d
+        return ref.view(B, N, sum(pyr.channels), 7).permute(0, 2, 3, 1).unsqueeze(2)   # (B,C,1,7,N)
+
+
+class IFNetFeatureExtractor(_ExtractorBase):
+    """32-res encoder (ifnet.py:64-120): 4 sampled levels, align_corners=True, displacement 0.035."""
+
+    displacement = 0.035
+    align_corners = True
+
+    def __init__(self, f1, f2, f3, f4):
+        super().__init__()
+        self.conv_1 = nn.Conv3d(1, f1, 3, padding=1)
+        self.conv_1_1 = nn.Conv3d(f1, f2, 3, padding=1)
+        self.conv_2 = nn.Conv3d(f2, f3, 3, padding=1)
+        self.conv_2_1 = nn.Conv3d(f3, f4, 3, padding=1)
+        self.conv_3 = nn.Conv3d(f4, f4, 3, padding=1)
+        self.conv_3_1 = nn.Conv3d(f4, f4, 3, padding=1)
+        self.actvn = nn.ReLU()
+        self.maxpool = nn.MaxPool3d(2)
+        self.conv1_1_bn = nn.BatchNorm3d(f2)
+        self.conv2_1_bn = nn.BatchNorm3d(f4)
+        self.conv3_1_bn = nn.BatchNorm3d(f4)
+        self.displacments = _displacements(self.displacement)
+
+    def encode(self, x):
+        stages = ((self.conv_1, self.conv_1_1, self.conv1_1_bn), (self.conv_2, self.conv_2_1, self.conv2_1_bn),
+                  (self.conv_3, self.conv_3_1, self.conv3_1_bn))
+        vols, net = [], x
+        for i, (ca, cb, bn) in enumerate(stages):
+            net = bn(self.actvn(cb(self.actvn(ca(net)))))
+            vols.append(net)
+            if i + 1 < len(stages):
+                net = self.maxpool(net)
+        return vols
+
+
+class IFNetFeatureExtractor128(_ExtractorBase):
+    """128-res encoder (ifnet.py:122-199): 6 sampled levels, align_corners=False, displacement 0.0722."""
+
+    displacement = 0.0722
+    align_corners = False
+
+    def __init__(self):
+        super().__init__()
+        self.conv_in = nn.Conv3d(1, 16, 3, padding=1)
+        self.conv_0 = nn.Conv3d(16, 32, 3, padding=1)
+        self.conv_0_1 = nn.Conv3d(32, 32, 3, padding=1)
+        self.conv_1 = nn.Conv3d(32, 64, 3, padding=1)
+        self.conv_1_1 = nn.Conv3d(64, 64, 3, padding=1)
+        self.conv_2 = nn.Conv3d(64, 128, 3, padding=1)
+        self.conv_2_1 = nn.Conv3d(128, 128, 3, padding=1)
+        self.conv_3 = nn.Conv3d(128, 128, 3, padding=1)
+        self.conv_3_1 = nn.Conv3d(128, 128, 3, padding=1)
+        self.actvn = nn.ReLU()
+        self.maxpool = nn.MaxPool3d(2)
+        self.conv_in_bn = nn.BatchNorm3d(16)
+        self.conv0_1_bn = nn.BatchNorm3d(32)
+        self.conv1_1_bn = nn.BatchNorm3d(64)
+        self.conv2_1_bn = nn.BatchNorm3d(128)
+        self.conv3_1_bn = nn.BatchNorm3d(128)
+        self.displacments = _displacements(self.displacement)
+
+    def encode(self, x):
+        net = self.conv_in_bn(self.actvn(self.conv_in(x)))
+        vols = [net]
+        for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
+                           (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):
+            net = self.maxpool(net)
+            net = bn(self.actvn(cb(self.actvn(ca(net)))))
+            vols.append(net)
+        return vols
+
+
+class IFNet(nn.Module):
+    """ifnet.py:10-61."""
+
+    def __init__(self, hidden_dim=256):
+        super().__init__()
+        if args.net_res == 128:
+            self.ifnet_feature_extractor = IFNetFeatureExtractor128()
+            feature_size = (1 + 16 + 32 + 64 + 128 + 128) * 7
+            self.fc_0 = nn.Conv1d(feature_size, hidden_dim, 1)
+            self.fc_1 = nn.Conv1d(hidden_dim, hidden_dim, 1)
+            self.fc_2 = nn.Conv1d(hidden_dim, hidden_dim, 1)
+        elif args.net_res == 32:
+            self.ifnet_feature_extractor = IFNetFeatureExtractor(32, 64, 128, 128)
+            feature_size = (1 + 64 + 128 + 128) * 7
+            self.fc_0 = nn.Conv1d(feature_size, hidden_dim * 2, 1)
+            self.fc_1 = nn.Conv1d(hidden_dim * 2, hidden_dim, 1)
+            self.fc_2 = nn.Conv1d(hidden_dim, hidden_dim, 1)
+        else:
+            # the reference *returns* NotImplementedError here (ifnet.py:31-32, a latent bug); raise instead
+            raise NotImplementedError(f"net_res={args.net_res}")
+        self.fc_out = nn.Conv1d(hidden_dim, 1, 1)
+        self.actvn = nn.ReLU()
+        self._packed = ops.PackedDecoder()
+
+    def query(self, x, vols, points):
+        """Hot path given precomputed volumes: stencil sampling + decoder -> logits (B,N)."""
+        pyr = self.ifnet_feature_extractor.pyramid(x, vols)
+        return ops.query(pyr, self._packed, points, x, self.fc_0.weight, self.fc_0.bias, self.fc_1.weight, self.fc_1.bias,
+                         self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, vols)
+
+    def forward(self, x, points):
+        vols = self.ifnet_feature_extractor.encode(x)
+        return self.query(x, vols, points)
+
+
+def make_3d_grid(bb_min, bb_max, shape, res_increase=None):
+    """ifnet.py:202-212: inclusive linspace lattice, flattened with the last axis fastest (CPU tensor)."""
+    if res_increase is None:
+        res_increase = args.inf_res
+    sx, sy, sz = (int(res_increase * int(s)) for s in shape)
+    px = torch.linspace(bb_min[0], bb_max[0], sx).view(-1, 1, 1).expand(sx, sy, sz)
+    py = torch.linspace(bb_min[1], bb_max[1], sy).view(1, -1, 1).expand(sx, sy, sz)
+    pz = torch.linspace(bb_min[2], bb_max[2], sz).view(1, 1, -1).expand(sx, sy, sz)
+    return torch.stack([px.reshape(-1), py.reshape(-1), pz.reshape(-1)], dim=1)
+
+
+def evaluate_network_on_grid(network, x, resolution, res_increase=None):
+    """ifnet.py:215-229.  For an :class:`IFNet` the encoder runs ONCE per call (the reference re-runs
+    it for each of the 512 chunks) and the chunks go through the query kernels only; any other
+    module is evaluated exactly like the reference does."""
+    if res_increase is None:
+        res_increase = args.inf_res
+    points_batch_size = args.num_points * args.batch_size
+    pointsf = make_3d_grid((-0.5,) * 3, (0.5,) * 3, resolution, res_increase)
+    shape = tuple(int(res_increase * int(r)) for r in resolution)
+    values = []
+    with torch.no_grad():
+        if isinstance(network, IFNet) and not network.training:
+            vols = network.ifnet_feature_extractor.encode(x)
+            big = max(points_batch_size, 1 << 20)
+            for pi in torch.split(pointsf, big):
+                pi = pi.unsqueeze(0).to(x.device).expand(x.shape[0], -1, -1).contiguous()
+                occ_hat = torch.sigmoid(network.query(x, vols, pi))
+                values.append(occ_hat[0].detach().cpu())
+        else:
+            for pi in torch.split(pointsf, points_batch_size):
+                pi = pi.unsqueeze(0).to(x.device)
+                occ_hat = torch.sigmoid(network(x, pi))
+                values.append(occ_hat.squeeze(0).detach().cpu())
+    value = torch.cat(values, dim=0).numpy()
+    return value.reshape(*shape)
+
+
+def implicit_to_mesh(network, x, resolution, threshold_p, output_path, res_increase=None):
+    """ifnet.py:232-234: marching cubes on 1 - occupancy (CPU, through the reference's own
+    ``util.visualize.visualize_sdf`` when it is importable)."""
+    value_grid = evaluate_network_on_grid(network, x, resolution, res_increase)
+    try:
+        from util.visualize import visualize_sdf  # type: ignore
+    except Exception as e:  # marching_cubes / trimesh are not part of this package
+        raise RuntimeError("implicit_to_mesh needs the reference's util.visualize (marching_cubes) on sys.path; "
+                           "use evaluate_network_on_grid for the occupancy grid") from e
+    visualize_sdf(1 - value_grid, output_path, level=threshold_p)

@@ -1,0 +1,385 @@
+"""Host side above the C ABI: torch.autograd.Functions that hand raw device pointers of torch
+tensors to libsvr_b200.so on the current CUDA stream.  PyTorch is plumbing here (device memory,
+streams, autograd graph); every kernel on the path is ours.  No CPU fallback: non-CUDA tensors are
+an error."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _abi
+
+_BF16 = torch.bfloat16
+
+
+def _lib():
+    return _abi.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"svr_b200: `{name}` must be a CUDA tensor (got {t.device}); there is no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# =================================================================================================
+# projection
+# =================================================================================================
+class _Unproject(torch.autograd.Function):
+    """depth (B,H,W) -> points (B,H*W,3); projection.py:150-163,201-206 (+ :124-132 when normalise)."""
+
+    @staticmethod
+    def forward(ctx, depth, f, cx, cy, scale, offset, dims, normalise):
+        depth = _dev_f32(depth, "depthmap")
+        B, H, W = depth.shape
+        pts = torch.empty((B, H * W, 3), device=depth.device, dtype=torch.float32)
+        _abi.check(_lib().svr_unproject_fwd(depth.data_ptr(), B, H, W, f, cx, cy, _abi.f32x3(scale), _abi.f32x3(offset),
+                                            _abi.i64x3(dims), int(normalise), pts.data_ptr(), _stream()), "unproject_fwd")
+        ctx.meta = (B, H, W, f, cx, cy, tuple(scale), tuple(dims), int(normalise))
+        return pts
+
+    @staticmethod
+    def backward(ctx, gpts):
+        B, H, W, f, cx, cy, scale, dims, normalise = ctx.meta
+        gpts = _dev_f32(gpts, "grad")
+        gd = torch.empty((B, H, W), device=gpts.device, dtype=torch.float32)
+        _abi.check(_lib().svr_unproject_bwd(gpts.data_ptr(), B, H, W, f, cx, cy, _abi.f32x3(scale), _abi.i64x3(dims),
+                                            normalise, gd.data_ptr(), _stream()), "unproject_bwd")
+        return gd, None, None, None, None, None, None, None
+
+
+def unproject(depth, f, cx, cy, scale, offset, dims, normalise=False):
+    return _Unproject.apply(depth, float(f), float(cx), float(cy), scale, offset, dims, normalise)
+
+
+def norm_grid_space_(pc: torch.Tensor, dims) -> torch.Tensor:
+    """In-place projection.py:124-132 on a contiguous CUDA tensor (B,P,3)."""
+    if not (pc.is_cuda and pc.dtype == torch.float32 and pc.is_contiguous()):
+        raise RuntimeError("svr_b200: norm_grid_space needs a contiguous fp32 CUDA tensor")
+    _abi.check(_lib().svr_norm_grid_space(pc.data_ptr(), pc.numel() // 3, _abi.i64x3(dims), _stream()), "norm_grid_space")
+    return pc
+
+
+class _Voxelize(torch.autograd.Function):
+    """project.pc_voxels (projection.py:39-80), bit-exact."""
+
+    @staticmethod
+    def forward(ctx, points, dims, eps, tail_start):
+        pts = _dev_f32(points, "points")
+        B, N, _ = pts.shape
+        d = _abi.i64x3(dims)
+        grid = torch.empty((B, int(dims[0]), int(dims[1]), int(dims[2])), device=pts.device, dtype=torch.float32)
+        need_grad = ctx.needs_input_grad[0]
+        sat = torch.empty(((grid.numel() + 31) // 32,), device=pts.device, dtype=torch.int32) if need_grad else None
+        ws_bytes = _lib().svr_voxelize_workspace_bytes(B, N, d)
+        ws = torch.empty((ws_bytes,), device=pts.device, dtype=torch.uint8)
+        _abi.check(_lib().svr_voxelize_fwd(pts.data_ptr(), B, N, d, float(eps), int(tail_start), grid.data_ptr(), _ptr(sat),
+                                           ws.data_ptr(), ws_bytes, _stream()), "voxelize_fwd")
+        ctx.save_for_backward(pts, sat)
+        ctx.meta = (B, N, tuple(int(x) for x in dims), float(eps))
+        return grid
+
+    @staticmethod
+    def backward(ctx, ggrid):
+        pts, sat = ctx.saved_tensors
+        B, N, dims, eps = ctx.meta
+        ggrid = _dev_f32(ggrid, "grad")
+        gp = torch.empty_like(pts)
+        _abi.check(_lib().svr_voxelize_bwd(pts.data_ptr(), ggrid.data_ptr(), _ptr(sat), B, N, _abi.i64x3(dims), eps,
+                                           gp.data_ptr(), _stream()), "voxelize_bwd")
+        return gp, None, None, None
+
+
+def voxelize(points, dims, eps=1e-6, tail_start=-1):
+    return _Voxelize.apply(points, dims, eps, tail_start)
+
+
+class _Blur(torch.autograd.Function):
+    """project.voxels_smooth (projection.py:102-117): taps_w acts on the last axis, taps_d on the first."""
+
+    @staticmethod
+    def forward(ctx, grid, taps_w, taps_h, taps_d):
+        g = _dev_f32(grid, "voxels")
+        tw, th, td = (_dev_f32(t.reshape(-1), "taps") for t in (taps_w, taps_h, taps_d))
+        B, D, H, W = g.shape
+        out = torch.empty_like(g)
+        tmp = torch.empty((2,) + tuple(g.shape), device=g.device, dtype=torch.float32)
+        _abi.check(_lib().svr_blur_fwd(g.data_ptr(), B, D, H, W, tw.data_ptr(), tw.numel(), th.data_ptr(), th.numel(),
+                                       td.data_ptr(), td.numel(), out.data_ptr(), tmp[0].data_ptr(), tmp[1].data_ptr(),
+                                       _stream()), "blur_fwd")
+        ctx.save_for_backward(g, tw, th, td)
+        ctx.shapes = (taps_w.shape, taps_h.shape, taps_d.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g, tw, th, td = ctx.saved_tensors
+        gout = _dev_f32(gout, "grad")
+        B, D, H, W = g.shape
+        gin = torch.empty_like(g)
+        gt = torch.empty((tw.numel() + th.numel() + td.numel(),), device=g.device, dtype=torch.float32)
+        tmp = torch.empty((4,) + tuple(g.shape), device=g.device, dtype=torch.float32)
+        _abi.check(_lib().svr_blur_bwd(g.data_ptr(), gout.data_ptr(), B, D, H, W, tw.data_ptr(), tw.numel(), th.data_ptr(),
+                                       th.numel(), td.data_ptr(), td.numel(), gin.data_ptr(), gt.data_ptr(), tmp.data_ptr(),
+                                       _stream()), "blur_bwd")
+        kw, kh = tw.numel(), th.numel()
+        sw, sh, sd = ctx.shapes
+        return gin, gt[:kw].reshape(sw), gt[kw:kw + kh].reshape(sh), gt[kw + kh:].reshape(sd)
+
+
+def blur(grid, taps_w, taps_h, taps_d):
+    return _Blur.apply(grid, taps_w, taps_h, taps_d)
+
+
+# =================================================================================================
+# IF-Net sampling + decoder
+# =================================================================================================
+class PyramidSpec:
+    """Static description of the sampled volumes of one forward call."""
+
+    def __init__(self, channels: Sequence[int], dims: Sequence[Sequence[int]], align_corners: bool, displacement: float):
+        self.channels = tuple(int(c) for c in channels)
+        self.dims = tuple(tuple(int(v) for v in d) for d in dims)
+        self.align_corners = bool(align_corners)
+        self.displacement = float(displacement)
+        self.c = _abi.make_pyramid(self.channels, self.dims, align_corners, displacement)
+        self.kp = _lib().svr_feature_kp(C.byref(self.c))
+        if self.kp <= 0:
+            raise RuntimeError("svr_b200: invalid pyramid: " + _lib().svr_last_error().decode())
+        self.k = 7 * sum(self.channels)
+
+
+def pack_volume(v: torch.Tensor) -> torch.Tensor:
+    """fp32 (B,C,D,H,W), any strides -> bf16 NDHWC contiguous (B,D,H,W,C)."""
+    if not v.is_cuda:
+        raise RuntimeError("svr_b200: feature volumes must be CUDA tensors; there is no CPU path")
+    if v.dtype != torch.float32:
+        v = v.float()
+    B, Cc, D, H, W = v.shape
+    out = torch.empty((B, D, H, W, Cc), device=v.device, dtype=_BF16)
+    s = v.stride()
+    _abi.check(_lib().svr_pack_volume(v.data_ptr(), B, Cc, D, H, W, s[0], s[1], s[2], s[3], s[4], out.data_ptr(), _stream()),
+               "pack_volume")
+    return out
+
+
+class PackedDecoder:
+    """bf16 copies of the decoder weights in kernel layout; refreshed when a parameter changes
+    (tracked through the tensors' version counters, so optimiser steps invalidate it)."""
+
+    def __init__(self):
+        self.key = None
+        self.t = {}
+
+    def get(self, pyr: PyramidSpec, w0, w1, w2):
+        key = (pyr.channels, pyr.align_corners, w0.data_ptr(), w0._version, w1.data_ptr(), w1._version, w2.data_ptr(),
+               w2._version)
+        if key != self.key:
+            dev = w0.device
+            h0, h1, h2 = w0.shape[0], w1.shape[0], w2.shape[0]
+            w0f, w1f, w2f = (_dev_f32(w.detach().reshape(w.shape[0], -1), "weight") for w in (w0, w1, w2))
+            if w0f.shape[1] != pyr.k:
+                raise RuntimeError(f"svr_b200: fc_0 expects {w0f.shape[1]} features, pyramid provides {pyr.k}")
+            t = {"w0p": torch.empty((h0, pyr.kp), device=dev, dtype=_BF16), "w0pT": torch.empty((pyr.kp, h0), device=dev, dtype=_BF16),
+                 "w1": torch.empty((h1, h0), device=dev, dtype=_BF16), "w1T": torch.empty((h0, h1), device=dev, dtype=_BF16),
+                 "w2": torch.empty((h2, h1), device=dev, dtype=_BF16), "w2T": torch.empty((h1, h2), device=dev, dtype=_BF16)}
+            st = _stream()
+            _abi.check(_lib().svr_pack_w0(w0f.data_ptr(), h0, C.byref(pyr.c), t["w0p"].data_ptr(), t["w0pT"].data_ptr(), st), "pack_w0")
+            _abi.check(_lib().svr_pack_matrix(w1f.data_ptr(), h1, h0, t["w1"].data_ptr(), t["w1T"].data_ptr(), st), "pack_matrix")
+            _abi.check(_lib().svr_pack_matrix(w2f.data_ptr(), h2, h1, t["w2"].data_ptr(), t["w2T"].data_ptr(), st), "pack_matrix")
+            self.t, self.key = t, key
+        return self.t
+
+
+def _gemm_nt(A, B, bias, M, N, K, flags, c_bf16=None, c_f32=None, ldc=0, mask=None, dot_w=None, dot_b=None, out_dot=None):
+    _abi.check(_lib().svr_gemm_nt(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _ptr(bias), M, N, K, flags, _ptr(c_bf16),
+                                  _ptr(c_f32), ldc, _ptr(mask), _ptr(dot_w), _ptr(dot_b), _ptr(out_dot), _stream()), "gemm_nt")
+
+
+def _gemm_tn(A, B, M, N, P, out, accumulate=False):
+    nbytes = _lib().svr_gemm_tn_workspace_bytes(M, N, P)
+    ws = torch.empty((nbytes,), device=A.device, dtype=torch.uint8)
+    _abi.check(_lib().svr_gemm_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, P, out.data_ptr(), out.stride(0),
+                                  int(accumulate), ws.data_ptr(), nbytes, _stream()), "gemm_tn")
+
+
+RELU, ST_BF16, ST_F32, MASK, DOT = 1, 2, 4, 8, 16
+
+
+def gather_features(points, x0, packed_vols: List[torch.Tensor], pyr: PyramidSpec) -> torch.Tensor:
+    """(B,N,3), (B,1,D,H,W), packed bf16 volumes -> (B*N, KP) bf16 features in kernel order."""
+    B, N, _ = points.shape
+    feat = torch.empty((B * N, pyr.kp), device=points.device, dtype=_BF16)
+    tbl = _abi.ptr_table([None] + [v.data_ptr() for v in packed_vols])
+    _abi.check(_lib().svr_gather_fwd(points.data_ptr(), B, N, x0.data_ptr(), tbl, C.byref(pyr.c), feat.data_ptr(), _stream()),
+               "gather_fwd")
+    return feat
+
+
+class _Query(torch.autograd.Function):
+    """IFNet.forward given the encoder's volumes (ifnet.py:38-61,156-197): stencil gather + decoder.
+
+    inputs: points (B,N,3), x (B,1,D,H,W), vols[1..L-1] fp32 (B,C,D,H,W), then the 8 decoder
+    parameters.  Returns logits (B,N) fp32."""
+
+    @staticmethod
+    def forward(ctx, pyr: PyramidSpec, cache: PackedDecoder, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
+        pts = _dev_f32(points, "points")
+        x0 = _dev_f32(x, "x")
+        B, N, _ = pts.shape
+        M = B * N
+        dev = pts.device
+        packed = [pack_volume(v) for v in vols]
+        W = cache.get(pyr, w0, w1, w2)
+        h0n, h1n, h2n = w0.shape[0], w1.shape[0], w2.shape[0]
+        b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
+        wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
+        feat = gather_features(pts, x0, packed, pyr)
+        h0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
+        h1 = torch.empty((M, h1n), device=dev, dtype=_BF16)
+        h2 = torch.empty((M, h2n), device=dev, dtype=_BF16)
+        logits = torch.empty((M,), device=dev, dtype=torch.float32)
+        _gemm_nt(feat, W["w0p"], b0f, M, h0n, pyr.kp, RELU | ST_BF16, c_bf16=h0, ldc=h0n)
+        _gemm_nt(h0, W["w1"], b1f, M, h1n, h0n, RELU | ST_BF16, c_bf16=h1, ldc=h1n)
+        _gemm_nt(h1, W["w2"], b2f, M, h2n, h1n, RELU | ST_BF16 | DOT, c_bf16=h2, ldc=h2n, dot_w=wof, dot_b=bof, out_dot=logits)
+        ctx.pyr, ctx.cache_t = pyr, W
+        ctx.vol_meta = [(v.shape, v.stride(), ctx.needs_input_grad[12 + i]) for i, v in enumerate(vols)]
+        ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[3], ctx.needs_input_grad[2]
+        ctx.shapes = (B, N, w0.shape, w1.shape, w2.shape, wo.shape)
+        ctx.save_for_backward(pts, x0, feat, h0, h1, h2, wof, *packed)
+        return logits.view(B, N)
+
+    @staticmethod
+    def backward(ctx, glogits):
+        pts, x0, feat, h0, h1, h2, wof, *packed = ctx.saved_tensors
+        pyr, W = ctx.pyr, ctx.cache_t
+        B, N, s0, s1, s2, so = ctx.shapes
+        M = B * N
+        dev = pts.device
+        h0n, h1n, h2n = s0[0], s1[0], s2[0]
+        dl = _dev_f32(glogits, "grad").reshape(-1)
+        st = _stream()
+        # fc_out + relu(fc_2) backward
+        dz2 = torch.empty((M, h2n), device=dev, dtype=_BF16)
+        gwo = torch.zeros((h2n,), device=dev, dtype=torch.float32)
+        gbo = torch.zeros((1,), device=dev, dtype=torch.float32)
+        _abi.check(_lib().svr_decoder_head_bwd(dl.data_ptr(), h2.data_ptr(), wof.data_ptr(), M, h2n, dz2.data_ptr(), gwo.data_ptr(),
+                                               gbo.data_ptr(), st), "decoder_head_bwd")
+
+        def colsum(a, n):
+            out = torch.empty((n,), device=dev, dtype=torch.float32)
+            _abi.check(_lib().svr_colsum_bf16(a.data_ptr(), M, n, a.stride(0), out.data_ptr(), 0, st), "colsum")
+            return out
+
+        gw2 = torch.empty((h2n, h1n), device=dev, dtype=torch.float32)
+        _gemm_tn(dz2, h1, h2n, h1n, M, gw2)
+        gb2 = colsum(dz2, h2n)
+        dz1 = torch.empty((M, h1n), device=dev, dtype=_BF16)
+        _gemm_nt(dz2, W["w2T"], None, M, h1n, h2n, ST_BF16 | MASK, c_bf16=dz1, ldc=h1n, mask=h1)
+        gw1 = torch.empty((h1n, h0n), device=dev, dtype=torch.float32)
+        _gemm_tn(dz1, h0, h1n, h0n, M, gw1)
+        gb1 = colsum(dz1, h1n)
+        dz0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
+        _gemm_nt(dz1, W["w1T"], None, M, h0n, h1n, ST_BF16 | MASK, c_bf16=dz0, ldc=h0n, mask=h0)
+        gw0p = torch.empty((h0n, pyr.kp), device=dev, dtype=torch.float32)
+        _gemm_tn(dz0, feat, h0n, pyr.kp, M, gw0p)
+        gw0 = torch.empty((h0n, pyr.k), device=dev, dtype=torch.float32)
+        _abi.check(_lib().svr_unpack_w0_grad(gw0p.data_ptr(), h0n, C.byref(pyr.c), gw0.data_ptr(), st), "unpack_w0_grad")
+        gb0 = colsum(dz0, h0n)
+        # d features, then scatter-add into the volumes
+        any_vol = any(m[2] for m in ctx.vol_meta)
+        gvols_out: List[Optional[torch.Tensor]] = [None] * len(packed)
+        gx = gp = None
+        if any_vol or ctx.x_needs or ctx.p_needs:
+            dfeat = torch.empty((M, pyr.kp), device=dev, dtype=_BF16)
+            _gemm_nt(dz0, W["w0pT"], None, M, pyr.kp, h0n, ST_BF16, c_bf16=dfeat, ldc=pyr.kp)
+            gbufs = []
+            for i, (shape, _, needs) in enumerate(ctx.vol_meta):
+                Bv, Cv, Dv, Hv, Wv = shape
+                gbufs.append(torch.zeros((Bv, Dv, Hv, Wv, Cv), device=dev, dtype=torch.float32) if needs else None)
+            if ctx.x_needs:
+                gx = torch.zeros_like(x0)
+            if ctx.p_needs:
+                gp = torch.zeros_like(pts)
+            vt = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
+            gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
+            _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
+                                             _ptr(gp), st), "gather_bwd")
+            gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
+        return (None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
+
+
+def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols):
+    return _Query.apply(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
+
+
+class _Gather(torch.autograd.Function):
+    """IFNetFeatureExtractor*.forward's sampling part as a standalone differentiable op returning
+    the kernel-order bf16 feature rows (B*N, KP)."""
+
+    @staticmethod
+    def forward(ctx, pyr: PyramidSpec, points, x, *vols):
+        pts = _dev_f32(points, "points")
+        x0 = _dev_f32(x, "x")
+        packed = [pack_volume(v) for v in vols]
+        feat = gather_features(pts, x0, packed, pyr)
+        ctx.pyr = pyr
+        ctx.vol_meta = [(v.shape, ctx.needs_input_grad[3 + i]) for i, v in enumerate(vols)]
+        ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[2], ctx.needs_input_grad[1]
+        ctx.save_for_backward(pts, x0, *packed)
+        return feat
+
+    @staticmethod
+    def backward(ctx, gfeat):
+        pts, x0, *packed = ctx.saved_tensors
+        pyr = ctx.pyr
+        B, N, _ = pts.shape
+        dev = pts.device
+        dfeat = gfeat.to(_BF16).contiguous()
+        gbufs = [torch.zeros((s[0], s[2], s[3], s[4], s[1]), device=dev, dtype=torch.float32) if needs else None
+                 for (s, needs) in ctx.vol_meta]
+        gx = torch.zeros_like(x0) if ctx.x_needs else None
+        gp = torch.zeros_like(pts) if ctx.p_needs else None
+        vt = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
+        gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
+        _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
+                                         _ptr(gp), _stream()), "gather_bwd")
+        return (None, gp, gx, *[g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs])
+
+
+def gather(pyr, points, x, vols):
+    return _Gather.apply(pyr, points, x, *vols)
+
+
+def feature_index_map(pyr: PyramidSpec, device) -> torch.Tensor:
+    """index tensor `idx` (K,) with reference feature k = c*7+d  ==  kernel-order column idx[k]."""
+    ks = []
+    ubase = 1
+    # level 0: channel 0, stencil d -> column d
+    cols = {}
+    for d in range(7):
+        cols[(0, d)] = d
+    coff = 1
+    for l in range(1, len(pyr.channels)):
+        upd = pyr.channels[l] // 8
+        for d in range(7):
+            for cc in range(pyr.channels[l]):
+                cols[(coff + cc, d)] = (ubase + d * upd + cc // 8) * 8 + cc % 8
+        ubase += 7 * upd
+        coff += pyr.channels[l]
+    for c in range(coff):
+        for d in range(7):
+            ks.append(cols[(c, d)])
+    return torch.tensor(ks, device=device, dtype=torch.long)
