@@ -158,7 +158,8 @@ def gen_ifnet(ref_ifnet, net_res: int):
     x = (torch.rand((B, 1) + dims, generator=g) < 0.15).float() * torch.rand((B, 1) + dims, generator=g)
     pts = (torch.rand((B, N, 3), generator=g) - 0.5) * 1.1
     occ = (torch.rand((B, N), generator=g) < 0.5).float()
-    out = {"dims": np.array(dims), "x": x.numpy(), "pts": pts.numpy(), "occ": occ.numpy()}
+    cot = torch.randn((B, N), generator=g)          # fixed upstream gradient for the VJP checks
+    out = {"dims": np.array(dims), "x": x.numpy(), "pts": pts.numpy(), "occ": occ.numpy(), "cot": cot.numpy()}
     for mode in ("train", "eval"):
         net.train(mode == "train")
         for k, v in sd.items():   # restore BN running stats mutated by the train pass
@@ -183,6 +184,20 @@ def gen_ifnet(ref_ifnet, net_res: int):
         out[f"{mode}_d_fc_0_b"] = net.fc_0.bias.grad.numpy().copy()
         first = "conv_in" if net_res == 128 else "conv_1"
         out[f"{mode}_d_{first}_w"] = getattr(net.ifnet_feature_extractor, first).weight.grad.numpy().copy()
+        # vector-Jacobian products for a FIXED cotangent (isolates the backward kernels from the
+        # loss non-linearity, which amplifies bf16 forward error)
+        for k, v in sd.items():
+            dict(net.state_dict())[k].copy_(v)
+        xx = x.clone().requires_grad_(True)
+        pp = pts.clone().requires_grad_(True)
+        net.zero_grad()
+        net(xx, pp).backward(cot)
+        out[f"{mode}_vjp_dx"] = xx.grad.numpy()
+        out[f"{mode}_vjp_dpts"] = pp.grad.numpy()
+        for nm in ("fc_out", "fc_2", "fc_1", "fc_0"):
+            out[f"{mode}_vjp_{nm}_w"] = getattr(net, nm).weight.grad.numpy()[:8].copy()
+            out[f"{mode}_vjp_{nm}_b"] = getattr(net, nm).bias.grad.numpy().copy()
+        out[f"{mode}_vjp_{first}_w"] = getattr(net.ifnet_feature_extractor, first).weight.grad.numpy().copy()
         # the restatement must agree
         sd2 = {k: v.clone() for k, v in sd.items()}
         mine = R.ifnet_forward(sd2, x, pts, net_res, training=(mode == "train"))

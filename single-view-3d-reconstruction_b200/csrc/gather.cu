@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
         bf16x8_to_float(*reinterpret_cast<const uint4 *>(dfeat + pt * P.kp + (int64_t)u * 8), g);
         if (level == 0) {
             const int64_t base = (int64_t)b * P.D[0] * P.H[0] * P.W[0];
-#pragma unroll 1
+#pragma unroll
             for (int dd = 0; dd < 7; ++dd) {
                 Corners c;
                 stencil_corners(P, 0, dd, px, py, pz, c);

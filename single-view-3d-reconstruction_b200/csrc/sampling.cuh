@@ -82,12 +82,16 @@ struct Corners {
 // model/ifnet.py:156-159 + F.grid_sample unnormalisation (ATen GridSampler.h:27-35)
 __device__ __forceinline__ void stencil_corners(const Pyr &P, int level, int d, float px, float py, float pz, Corners &c) {
     // point coords are (D,H,W)-ordered; grid_sample's x indexes W, y indexes H, z indexes D
-    float q[3] = {__fmul_rn(2.0f, pz), __fmul_rn(2.0f, py), __fmul_rn(2.0f, px)};
-    if (d > 0) {
-        int axis = (d - 1) >> 1;
-        float s = ((d - 1) & 1) ? P.delta : -P.delta;
-        q[axis] = __fadd_rn(q[axis], s);
-    }
+    // displacement order (ifnet.py:144-153): d=1,2 -> x -/+, d=3,4 -> y -/+, d=5,6 -> z -/+
+    // (selects instead of a dynamically indexed local array: everything stays in registers)
+    const float sgn = (d & 1) ? -P.delta : P.delta;
+    float q[3];
+    q[0] = __fmul_rn(2.0f, pz);
+    q[1] = __fmul_rn(2.0f, py);
+    q[2] = __fmul_rn(2.0f, px);
+    if (d == 1 || d == 2) q[0] = __fadd_rn(q[0], sgn);
+    if (d == 3 || d == 4) q[1] = __fadd_rn(q[1], sgn);
+    if (d == 5 || d == 6) q[2] = __fadd_rn(q[2], sgn);
     const int size[3] = {P.W[level], P.H[level], P.D[level]};
     float idx[3];
 #pragma unroll

@@ -5,6 +5,7 @@ zero logits); gradients get the same per-tensor bound."""
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import c_oracle as CO
 from oracle import ref_torch as R
@@ -48,30 +49,112 @@ def test_feature_gather_vs_golden_and_oracle(golden, net_res):
     assert np.abs(head[:, 0] - ref[:, 0]).max() < 4e-3
 
 
+def _rel_l2(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def _cos(a, b):
+    a, b = torch.as_tensor(a).float().cpu().reshape(-1), torch.as_tensor(b).float().cpu().reshape(-1)
+    return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _bf16_pipeline_reference(sd, x, vols, pts, cot, net_res):
+    """torch restatement of the device pipeline WITH its rounding points (volumes, features, weights,
+    hidden activations and dz in bf16; fp32 accumulation): F.grid_sample + fp32 matmuls on the GPU.
+    Returns logits and every gradient the hot path produces."""
+    delta = R.DISPLACEMENT_128 if net_res == 128 else R.DISPLACEMENT_32
+    ac = net_res != 128
+    xr = x.detach().clone().requires_grad_(True)
+    pr = pts.detach().clone().requires_grad_(True)
+    vr = [_bf(v.detach()).requires_grad_(True) for v in vols]
+    grid = R.stencil_grid(pr, delta)
+    feat = torch.cat([F.grid_sample(v, grid, align_corners=ac) for v in [xr] + vr], dim=1)       # (B,C,1,7,N)
+    B, C, _, S, N = feat.shape
+    f32 = feat[:, :, 0].permute(0, 3, 1, 2).reshape(B * N, C * S)                                    # k = c*7+d
+    Fb = _bf(f32.detach())
+    W = {k: _bf(sd[k].cuda().reshape(sd[k].shape[0], -1)) for k in ("fc_0.weight", "fc_1.weight", "fc_2.weight")}
+    b = {k: sd[k].cuda() for k in ("fc_0.bias", "fc_1.bias", "fc_2.bias", "fc_out.bias")}
+    wo = sd["fc_out.weight"].cuda().reshape(-1)
+    h0 = torch.relu(Fb @ W["fc_0.weight"].t() + b["fc_0.bias"]); h0b = _bf(h0)
+    h1 = torch.relu(h0b @ W["fc_1.weight"].t() + b["fc_1.bias"]); h1b = _bf(h1)
+    h2 = torch.relu(h1b @ W["fc_2.weight"].t() + b["fc_2.bias"]); h2b = _bf(h2)
+    logits = (h2 @ wo + b["fc_out.bias"]).view(B, N)
+    dl = cot.reshape(-1)
+    g = {"fc_out.weight": (dl[:, None] * h2b).sum(0), "fc_out.bias": dl.sum()[None]}
+    dz2 = _bf(dl[:, None] * wo[None] * (h2b > 0))
+    g["fc_2.weight"], g["fc_2.bias"] = dz2.t() @ h1b, dz2.sum(0)
+    dz1 = _bf((dz2 @ W["fc_2.weight"]) * (h1b > 0))
+    g["fc_1.weight"], g["fc_1.bias"] = dz1.t() @ h0b, dz1.sum(0)
+    dz0 = _bf((dz1 @ W["fc_1.weight"]) * (h0b > 0))
+    g["fc_0.weight"], g["fc_0.bias"] = dz0.t() @ Fb, dz0.sum(0)
+    dF = _bf(dz0 @ W["fc_0.weight"])
+    f32.backward(dF)
+    g["dx"], g["dpts"] = xr.grad, pr.grad
+    for i, v in enumerate(vr):
+        g[f"dvol{i + 1}"] = v.grad
+    return logits.detach(), g
+
+
 @pytest.mark.parametrize("net_res", [128, 32])
 @pytest.mark.parametrize("mode", ["eval", "train"])
 def test_logits_and_gradients_vs_golden(golden, net_res, mode):
+    """Forward: logits within 1e-2 (max|d|/max|ref|) of the UNMODIFIED reference (measured 1e-3 .. 5e-3).
+
+    Backward, two checks per tensor (north_star states no number for gradients):
+      (1) against a torch restatement of the same pipeline with the same bf16 rounding points:
+          <= 3e-2 relative L2 (measured 1e-3 .. 1.4e-2; the residue is ReLU flips caused by 1-bf16-ulp
+          differences between F.grid_sample and the gather) -- the parity bar for the backward kernels;
+      (2) against the unmodified fp32 reference (golden VJPs): cosine similarity >= 0.98.  An
+          element-wise bound is not meaningful there: ReLU decisions taken on bf16-rounded
+          pre-activations flip for ~0.3 % of the units, which alone is ~7 % relative L2 (the
+          reference's own AMP path has the same property)."""
     g, sd = _case(golden, net_res)
     net = _net(net_res, sd)
     net.train(mode == "train")
     x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
     pts = torch.from_numpy(g["pts"]).cuda().requires_grad_(True)
     occ = torch.from_numpy(g["occ"]).cuda()
+    cot = torch.from_numpy(g["cot"]).cuda()
     logits = net(x, pts)
     assert logits.shape == occ.shape and logits.dtype == torch.float32
     assert _rel(logits.detach(), g[f"{mode}_logits"]) < TOL_BF16
     loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, occ, reduction="none").sum(-1).mean()
-    assert abs(float(loss) - float(g[f"{mode}_loss"])) / float(g[f"{mode}_loss"]) < TOL_BF16
-    loss.backward()
+    assert abs(float(loss.detach()) - float(g[f"{mode}_loss"])) / float(g[f"{mode}_loss"]) < TOL_BF16
+    logits.backward(cot)
     first = "conv_in" if net_res == 128 else "conv_1"
-    checks = {
-        "d_fc_out_w": net.fc_out.weight.grad, "d_fc_out_b": net.fc_out.bias.grad, "d_fc_2_w_head": net.fc_2.weight.grad[:8],
-        "d_fc_1_b": net.fc_1.bias.grad, "d_fc_0_w_head": net.fc_0.weight.grad[:4], "d_fc_0_b": net.fc_0.bias.grad,
-        f"d_{first}_w": getattr(net.ifnet_feature_extractor, first).weight.grad, "dx": x.grad, "dpts": pts.grad,
-    }
+    checks = {"dx": x.grad, "dpts": pts.grad, f"{first}_w": getattr(net.ifnet_feature_extractor, first).weight.grad}
+    for nm in ("fc_out", "fc_2", "fc_1", "fc_0"):
+        checks[f"{nm}_w"] = getattr(net, nm).weight.grad[:8]
+        checks[f"{nm}_b"] = getattr(net, nm).bias.grad
     for name, got in checks.items():
-        r = _rel(got, g[f"{mode}_{name}"])
-        assert r < 3 * TOL_BF16, (name, r)
+        c = _cos(got, g[f"{mode}_vjp_{name}"])
+        assert c > 0.98, (name, c)
+    # (1) hot path on the same device volumes vs the bf16-pipeline restatement
+    with torch.no_grad():
+        vols = net.ifnet_feature_extractor.encode(x.detach()) if mode == "eval" else None
+    if vols is None:
+        return   # train-mode BN updates running stats on every encode; the eval cases cover (1)
+    net.zero_grad()
+    x2 = x.detach().clone().requires_grad_(True)
+    p2 = pts.detach().clone().requires_grad_(True)
+    v2 = [_bf(v).requires_grad_(True) for v in vols]
+    l2 = net.query(x2, v2, p2)
+    l2.backward(cot)
+    ref_logits, rg = _bf16_pipeline_reference(sd, x, vols, pts, cot, net_res)
+    assert _rel(l2.detach(), ref_logits) < 2e-3
+    for nm in ("fc_out", "fc_2", "fc_1", "fc_0"):
+        mod = getattr(net, nm)
+        assert _rel_l2(mod.weight.grad.reshape(mod.weight.shape[0], -1), rg[f"{nm}.weight"].reshape(mod.weight.shape[0], -1)) < 3e-2, nm
+        assert _rel_l2(mod.bias.grad, rg[f"{nm}.bias"]) < 3e-2, nm
+    assert _rel_l2(x2.grad, rg["dx"]) < 3e-2
+    assert _rel_l2(p2.grad, rg["dpts"]) < 3e-2
+    for i, v in enumerate(v2):
+        assert _rel_l2(v.grad, rg[f"dvol{i + 1}"]) < 3e-2, i
 
 
 def test_out_of_range_points_and_zero_padding():
