@@ -72,6 +72,71 @@ _SIGS = {
 EXPORTS = tuple(_SIGS)
 _lib = None
 
+# kernels launched per entry point (memsets are not kernels of ours and are not counted)
+KERNELS_PER_CALL = {
+    "svr_unproject_fwd": 1, "svr_unproject_bwd": 1, "svr_norm_grid_space": 1, "svr_voxelize_fwd": 7, "svr_voxelize_bwd": 1,
+    "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
+    "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 1, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
+    "svr_decoder_head_bwd": 2, "svr_colsum_bf16": 2, "svr_query_fwd_fused": 1, "svr_dense_eval": 1,
+}
+
+
+class Profile:
+    """Optional instrumentation used by bench.py: counts kernel launches per entry point and, when
+    ``events`` is enabled, brackets every call with CUDA events on the current torch stream."""
+
+    def __init__(self):
+        self.launches = {}
+        self.calls = {}
+        self.events = None          # None = off; dict name -> [(start, end)]
+
+    def reset(self, with_events=False):
+        self.launches, self.calls = {}, {}
+        self.events = {} if with_events else None
+
+    def total_launches(self):
+        return sum(self.launches.values())
+
+    def kernel_ms(self):
+        """name -> (calls, total ms); needs a device synchronize before."""
+        out = {}
+        for name, evs in (self.events or {}).items():
+            out[name] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+        return out
+
+
+PROFILE = Profile()
+
+
+class _Lib:
+    """Thin proxy over the CDLL: same call syntax, plus the Profile bookkeeping."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in _SIGS:
+            setattr(self, name, self._wrap(name, getattr(cdll, name)))
+
+    @staticmethod
+    def _wrap(name, fn):
+        n_k = KERNELS_PER_CALL.get(name, 0)
+        if n_k == 0:
+            return fn
+
+        def call(*a):
+            prof = PROFILE
+            prof.launches[name] = prof.launches.get(name, 0) + n_k
+            prof.calls[name] = prof.calls.get(name, 0) + 1
+            if prof.events is None:
+                return fn(*a)
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            prof.events.setdefault(name, []).append((e0, e1))
+            return rc
+        return call
+
 
 def load():
     """Load the library (once) and attach the signatures.  Raises if it is not there."""
@@ -89,8 +154,8 @@ def load():
         fn.argtypes = args
     if lib.svr_abi_version() != 1:
         raise RuntimeError(f"svr_b200: ABI version mismatch ({lib.svr_abi_version()} != 1)")
-    _lib = lib
-    return lib
+    _lib = _Lib(lib)
+    return _lib
 
 
 def check(rc: int, what: str = ""):
