@@ -157,23 +157,30 @@ int svr_decoder_head_bwd(const float *dlogit, const uint16_t *h2, const float *w
 /* column sums of a bf16 (M,N) matrix into fp32 out[N] (bias gradients); accumulate != 0 adds.    */
 int svr_colsum_bf16(const uint16_t *a, int M, int N, int64_t lda, float *out, int accumulate, void *stream);
 
-/* Fused forward: gather -> smem -> tcgen05 fc_0 -> fc_1 -> fc_2 -> fc_out in ONE kernel (128-net,
- * hidden 256).  logits (B*N) fp32.  If save_h != NULL the three hidden activations (post-ReLU,
- * bf16, (B*N,256) each, concatenated) and, if save_feat != NULL, the gathered features are kept
- * for the backward.  Implemented in fused_query.cu.                                              */
+/* Fused forward: gather -> smem -> tcgen05 fc_0 -> fc_1 -> fc_2 -> fc_out in ONE persistent kernel
+ * (128-net and any pyramid whose decoder has hidden size 256).  Weights are passed as pre-swizzled
+ * UMMA chunk images (svr_pack_decoder_image of the bf16 row-major matrices: fc_0 in K' order).
+ * logits (B*N) fp32, indexed like `points`.  perm (optional, B*N ints): processing order, row r of
+ * the kernel handles point perm[r] (spatially sorted points make the gather cache-friendly);
+ * save_h (optional): post-ReLU hidden activations bf16 (3, B*N, 256) in ROW order; save_feat
+ * (optional): gathered features bf16 (B*N, KP) in ROW order -- both feed the backward.           */
 typedef struct svr_decoder_weights {
-    const uint16_t *w0p;   /* (H0, KP) bf16, K' order   */
-    const uint16_t *w1;    /* (H1, H0) bf16             */
-    const uint16_t *w2;    /* (H2, H1) bf16             */
+    const void *w0p;       /* image of (256, KP) bf16, K' order                                   */
+    const void *w1;        /* image of (256, 256) bf16                                            */
+    const void *w2;        /* image of (256, 256) bf16                                            */
     const float *b0, *b1, *b2;
-    const float *wout;     /* (H2) fp32                 */
-    const float *bout;     /* (1) fp32, device          */
+    const float *wout;     /* (256) fp32                                                          */
+    const float *bout;     /* (1) fp32, device                                                    */
     int h0, h1, h2;
 } svr_decoder_weights;
 
-int svr_query_fwd_fused(const float *points, int B, int N, const float *x0, const uint16_t *const *vols_host,
-                        const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, float *logits,
-                        uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream);
+/* bf16 row-major (R, K) -> K/64 chunks of (R x 128 B) in the 128B-swizzled K-major UMMA layout   */
+int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *image, void *stream);
+
+int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, const float *x0,
+                        const uint16_t *const *vols_host, const svr_pyramid *pyr_host,
+                        const svr_decoder_weights *w_host, float *logits, uint16_t *save_h,
+                        uint16_t *save_feat, int apply_sigmoid, void *stream);
 
 /* Dense evaluation (evaluate_network_on_grid, ifnet.py:215-229; make_3d_grid :202-212): evaluates
  * sigmoid(decoder(sample(x, lattice))) on the (sx,sy,sz) inclusive lattice over [-0.5,0.5]^3 for

@@ -487,7 +487,7 @@ int svr_decoder_head_bwd(const float *dlogit, const uint16_t *h2, const float *w
     SVR_REQUIRE(Hd > 0 && Hd <= 256, "decoder_head_bwd: hidden size must be <= 256");
     if (M == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    const int rows_per_block = 256;
+    const int rows_per_block = ceil_div(M, 4 * sm_count()) > 16 ? ceil_div(M, 4 * sm_count()) : 16;
     const int nblocks = ceil_div(M, rows_per_block);
     float *scratch = nullptr;
     if (int rc = scratch_alloc(&scratch, (size_t)nblocks * (Hd + 1), st)) return rc;
@@ -506,7 +506,7 @@ int svr_colsum_bf16(const uint16_t *a, int M, int N, int64_t lda, float *out, in
         if (!accumulate) SVR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
         return 0;
     }
-    const int rows_per_block = 512;
+    const int rows_per_block = ceil_div(M, 2 * sm_count()) > 16 ? ceil_div(M, 2 * sm_count()) : 16;
     const int nblocks = ceil_div(M, rows_per_block);
     float *scratch = nullptr;
     if (int rc = scratch_alloc(&scratch, (size_t)nblocks * N, st)) return rc;

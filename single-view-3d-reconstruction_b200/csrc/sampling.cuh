@@ -139,14 +139,12 @@ __device__ __forceinline__ uint4 float8_to_bf16(const float (&f)[8]) {
 
 // One unit of the feature row of a point: 8 bf16 values packed in a uint4.
 //   x0_b  : level-0 grid of the point's scene (fp32, D*H*W)
-//   vol_b : per-level bf16 NDHWC volume base of the point's scene (index 0 unused)
-__device__ __forceinline__ uint4 gather_unit(const Pyr &P, int u, float px, float py, float pz, const float *__restrict__ x0_b,
-                                             const __nv_bfloat16 *const *vol_b) {
-    int level, d, c0;
+//   vol_l : bf16 NDHWC volume base of the point's scene for `level` (unused for level 0)
+__device__ __forceinline__ uint4 gather_unit_decoded(const Pyr &P, int level, int d, int c0, float px, float py, float pz,
+                                                     const float *__restrict__ x0_b, const __nv_bfloat16 *__restrict__ vol_l) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (!decode_unit(P, u, level, d, c0)) return make_uint4(0, 0, 0, 0);
     if (level == 0) {
 #pragma unroll
         for (int dd = 0; dd < 7; ++dd) {
@@ -169,7 +167,7 @@ __device__ __forceinline__ uint4 gather_unit(const Pyr &P, int u, float px, floa
     }
     Corners c;
     stencil_corners(P, level, d, px, py, pz, c);
-    const __nv_bfloat16 *vb = vol_b[level] + c0;
+    const __nv_bfloat16 *vb = vol_l + c0;
     const int C = P.C[level];
     uint4 raw[8];
     float w[8];
@@ -190,6 +188,13 @@ __device__ __forceinline__ uint4 gather_unit(const Pyr &P, int u, float px, floa
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[k], acc[j]);
     }
     return float8_to_bf16(acc);
+}
+
+__device__ __forceinline__ uint4 gather_unit(const Pyr &P, int u, float px, float py, float pz, const float *__restrict__ x0_b,
+                                             const __nv_bfloat16 *const *vol_b) {
+    int level, d, c0;
+    if (!decode_unit(P, u, level, d, c0)) return make_uint4(0, 0, 0, 0);
+    return gather_unit_decoded(P, level, d, c0, px, py, pz, x0_b, level > 0 ? vol_b[level] : nullptr);
 }
 #endif  // __CUDACC__
 

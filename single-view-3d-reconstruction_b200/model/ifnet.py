@@ -210,10 +210,14 @@ def evaluate_network_on_grid(network, x, resolution, res_increase=None):
         if isinstance(network, IFNet) and not network.training:
             vols = network.ifnet_feature_extractor.encode(x)
             big = max(points_batch_size, 1 << 20)
-            for pi in torch.split(pointsf, big):
-                pi = pi.unsqueeze(0).to(x.device).expand(x.shape[0], -1, -1).contiguous()
-                occ_hat = torch.sigmoid(network.query(x, vols, pi))
-                values.append(occ_hat[0].detach().cpu())
+            try:
+                for ci, pi in enumerate(torch.split(pointsf, big)):
+                    pi = pi.unsqueeze(0).to(x.device).expand(x.shape[0], -1, -1).contiguous()
+                    occ_hat = torch.sigmoid(network.query(x, vols, pi))
+                    network._packed.frozen = True          # weights cannot change between chunks
+                    values.append(occ_hat[0].detach().cpu())
+            finally:
+                network._packed.frozen = False
         else:
             for pi in torch.split(pointsf, points_batch_size):
                 pi = pi.unsqueeze(0).to(x.device)

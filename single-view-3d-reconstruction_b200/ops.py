@@ -176,17 +176,19 @@ def pack_volume(v: torch.Tensor) -> torch.Tensor:
 
 
 class PackedDecoder:
-    """bf16 copies of the decoder weights in kernel layout; refreshed when a parameter changes
-    (tracked through the tensors' version counters, so optimiser steps invalidate it)."""
+    """bf16 copies of the decoder weights in kernel layout.  Re-packed on EVERY call (three tiny
+    kernels, ~10 us) unless ``frozen`` is set: fused optimisers update parameters without bumping
+    the tensors' version counters, so no cheap staleness test is reliable.  ``frozen`` is used by
+    the chunked dense evaluation, where the weights cannot change between chunks."""
 
     def __init__(self):
         self.key = None
         self.t = {}
+        self.frozen = False
 
     def get(self, pyr: PyramidSpec, w0, w1, w2):
-        key = (pyr.channels, pyr.align_corners, w0.data_ptr(), w0._version, w1.data_ptr(), w1._version, w2.data_ptr(),
-               w2._version)
-        if key != self.key:
+        key = (pyr.channels, pyr.align_corners, w0.data_ptr(), w1.data_ptr(), w2.data_ptr())
+        if key != self.key or not self.frozen:
             dev = w0.device
             h0, h1, h2 = w0.shape[0], w1.shape[0], w2.shape[0]
             w0f, w1f, w2f = (_dev_f32(w.detach().reshape(w.shape[0], -1), "weight") for w in (w0, w1, w2))
@@ -199,6 +201,12 @@ class PackedDecoder:
             _abi.check(_lib().svr_pack_w0(w0f.data_ptr(), h0, C.byref(pyr.c), t["w0p"].data_ptr(), t["w0pT"].data_ptr(), st), "pack_w0")
             _abi.check(_lib().svr_pack_matrix(w1f.data_ptr(), h1, h0, t["w1"].data_ptr(), t["w1T"].data_ptr(), st), "pack_matrix")
             _abi.check(_lib().svr_pack_matrix(w2f.data_ptr(), h2, h1, t["w2"].data_ptr(), t["w2T"].data_ptr(), st), "pack_matrix")
+            if h0 == h1 == h2 == 256:    # pre-swizzled UMMA chunk images for the fused forward kernel
+                for name in ("w0p", "w1", "w2"):
+                    img = torch.empty((t[name].numel() * 2,), device=dev, dtype=torch.uint8)
+                    _abi.check(_lib().svr_pack_decoder_image(t[name].data_ptr(), t[name].shape[0], t[name].shape[1], img.data_ptr(), st),
+                               "pack_decoder_image")
+                    t[name + "_img"] = img
             self.t, self.key = t, key
         return self.t
 
@@ -216,6 +224,26 @@ def _gemm_tn(A, B, M, N, P, out, accumulate=False):
 
 
 RELU, ST_BF16, ST_F32, MASK, DOT = 1, 2, 4, 8, 16
+USE_FUSED = True     # fused gather+decoder forward kernel when the decoder is 256/256/256
+
+
+def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, sigmoid: bool = False, perm=None):
+    """One launch: gather -> tcgen05 decoder.  Returns (logits (M,), h (3,M,256) or None, feat (M,KP) or None)."""
+    B, N, _ = pts.shape
+    M = B * N
+    dev = pts.device
+    dw = _abi.DecoderWeights()
+    dw.w0p, dw.w1, dw.w2 = W["w0p_img"].data_ptr(), W["w1_img"].data_ptr(), W["w2_img"].data_ptr()
+    dw.b0, dw.b1, dw.b2 = b0f.data_ptr(), b1f.data_ptr(), b2f.data_ptr()
+    dw.wout, dw.bout = wof.data_ptr(), bof.data_ptr()
+    dw.h0 = dw.h1 = dw.h2 = 256
+    logits = torch.empty((M,), device=dev, dtype=torch.float32)
+    h = torch.empty((3, M, 256), device=dev, dtype=_BF16) if save else None
+    feat = torch.empty((M, pyr.kp), device=dev, dtype=_BF16) if save else None
+    tbl = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
+    _abi.check(_lib().svr_query_fwd_fused(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), tbl, C.byref(pyr.c), C.byref(dw),
+                                          logits.data_ptr(), _ptr(h), _ptr(feat), int(sigmoid), _stream()), "query_fwd_fused")
+    return logits, h, feat
 
 
 def gather_features(points, x0, packed_vols: List[torch.Tensor], pyr: PyramidSpec) -> torch.Tensor:
@@ -246,14 +274,21 @@ class _Query(torch.autograd.Function):
         h0n, h1n, h2n = w0.shape[0], w1.shape[0], w2.shape[0]
         b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
         wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
-        feat = gather_features(pts, x0, packed, pyr)
-        h0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
-        h1 = torch.empty((M, h1n), device=dev, dtype=_BF16)
-        h2 = torch.empty((M, h2n), device=dev, dtype=_BF16)
-        logits = torch.empty((M,), device=dev, dtype=torch.float32)
-        _gemm_nt(feat, W["w0p"], b0f, M, h0n, pyr.kp, RELU | ST_BF16, c_bf16=h0, ldc=h0n)
-        _gemm_nt(h0, W["w1"], b1f, M, h1n, h0n, RELU | ST_BF16, c_bf16=h1, ldc=h1n)
-        _gemm_nt(h1, W["w2"], b2f, M, h2n, h1n, RELU | ST_BF16 | DOT, c_bf16=h2, ldc=h2n, dot_w=wof, dot_b=bof, out_dot=logits)
+        needs_bwd = any(ctx.needs_input_grad)
+        if USE_FUSED and "w0p_img" in W:
+            logits, hs, feat = fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save=needs_bwd)
+            if not needs_bwd:
+                return logits.view(B, N)
+            h0, h1, h2 = hs[0], hs[1], hs[2]
+        else:
+            feat = gather_features(pts, x0, packed, pyr)
+            h0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
+            h1 = torch.empty((M, h1n), device=dev, dtype=_BF16)
+            h2 = torch.empty((M, h2n), device=dev, dtype=_BF16)
+            logits = torch.empty((M,), device=dev, dtype=torch.float32)
+            _gemm_nt(feat, W["w0p"], b0f, M, h0n, pyr.kp, RELU | ST_BF16, c_bf16=h0, ldc=h0n)
+            _gemm_nt(h0, W["w1"], b1f, M, h1n, h0n, RELU | ST_BF16, c_bf16=h1, ldc=h1n)
+            _gemm_nt(h1, W["w2"], b2f, M, h2n, h1n, RELU | ST_BF16 | DOT, c_bf16=h2, ldc=h2n, dot_w=wof, dot_b=bof, out_dot=logits)
         ctx.pyr, ctx.cache_t = pyr, W
         ctx.vol_meta = [(v.shape, v.stride(), ctx.needs_input_grad[12 + i]) for i, v in enumerate(vols)]
         ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[3], ctx.needs_input_grad[2]
