@@ -130,10 +130,16 @@ int svr_gather_fwd(const float *points, int B, int N, const float *x0, const uin
                    const svr_pyramid *pyr_host, uint16_t *feat, void *stream);
 /* Backward of the gather: dfeat (B*N, KP) bf16 -> scatter-add into gvols[l] (fp32 NDHWC, l>=1),
  * gx0 (fp32, may be NULL) and gpoints (B,N,3; may be NULL, needs x0/vols).  Outputs are
- * accumulated into (caller zero-fills).                                                          */
-int svr_gather_bwd(const float *points, int B, int N, const float *x0, const uint16_t *const *vols_host,
-                   const svr_pyramid *pyr_host, const uint16_t *dfeat, float *gx0, float *const *gvols_host,
-                   float *gpoints, void *stream);
+ * accumulated into (caller zero-fills).  perm (optional): row r of dfeat belongs to point perm[r]. */
+int svr_gather_bwd(const float *points, const int *perm, int B, int N, const float *x0,
+                   const uint16_t *const *vols_host, const svr_pyramid *pyr_host, const uint16_t *dfeat,
+                   float *gx0, float *const *gvols_host, float *gpoints, void *stream);
+
+/* Processing order for the query kernels: perm (B*N ints) lists point indices sorted by (scene,
+ * Morton code of a 16^3 cell), so that consecutive rows are spatial neighbours (cache locality of
+ * the gather; the reference has no counterpart -- every row is independent, results do not change).*/
+size_t svr_sort_points_workspace_bytes(int B, int N);
+int svr_sort_points(const float *points, int B, int N, int *perm, void *workspace, size_t workspace_bytes, void *stream);
 
 /* tcgen05 GEMMs (Conv1d k=1 of ifnet.py:55-59 and their backward).
  * NT:  C[M,N] = epi( A[M,K] . B[N,K]^T + bias[N] ),  A,B bf16 row-major, K % 64 == 0.
@@ -151,9 +157,9 @@ int svr_gemm_tn(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, 
 
 /* Small fused helpers of the decoder backward.
  * dz2[m,n] = dlogit[m] * wout[n] * (h2[m,n] > 0)  (bf16 out); gwout[n] += sum_m dlogit[m]*h2[m,n];
- * gbout += sum_m dlogit[m].                                                                      */
-int svr_decoder_head_bwd(const float *dlogit, const uint16_t *h2, const float *wout, int M, int Hd,
-                         uint16_t *dz2, float *gwout, float *gbout, void *stream);
+ * gbout += sum_m dlogit[m].  perm (optional): row m reads dlogit[perm[m]].                        */
+int svr_decoder_head_bwd(const float *dlogit, const int *perm, const uint16_t *h2, const float *wout, int M,
+                         int Hd, uint16_t *dz2, float *gwout, float *gbout, void *stream);
 /* column sums of a bf16 (M,N) matrix into fp32 out[N] (bias gradients); accumulate != 0 adds.    */
 int svr_colsum_bf16(const uint16_t *a, int M, int N, int64_t lda, float *out, int accumulate, void *stream);
 

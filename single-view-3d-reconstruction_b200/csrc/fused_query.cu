@@ -174,9 +174,9 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
             named_bar_sync(1, FQ_GATHER_THREADS);
             for (int kc = 0; kc < KC0; ++kc, ++gc) {
                 const int st = gc % FQ_NA;
-                int level, d, c0;
                 const int u = kc * 8 + unit_in_chunk;
-                const bool real = decode_unit(p.P, u, level, d, c0);
+                UnitCtx uc;
+                make_unit_ctx(p.P, u, p.vols.v, uc);
                 mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
                 uint8_t *a_st = s.a + st * FQ_A_BYTES;
 #pragma unroll 2
@@ -184,14 +184,13 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
                     const float4 q = pts_s[r];
                     const int scene = __float_as_int(q.w);
                     uint4 val = make_uint4(0, 0, 0, 0);
-                    if (real && scene >= 0) {
-                        const __nv_bfloat16 *vb[SVR_MAX_LEVELS];
-#pragma unroll
-                        for (int l = 0; l < SVR_MAX_LEVELS; ++l) vb[l] = nullptr;
-                        const float *x0b = p.x0 + (int64_t)scene * p.P.D[0] * p.P.H[0] * p.P.W[0];
-                        if (level > 0)
-                            vb[level] = p.vols.v[level] + (int64_t)scene * p.P.D[level] * p.P.H[level] * p.P.W[level] * p.P.C[level];
-                        val = gather_unit_decoded(p.P, level, d, c0, q.x, q.y, q.z, x0b, level > 0 ? vb[level] : nullptr);
+                    if (uc.real && scene >= 0) {
+                        if (uc.level > 0) {
+                            val = gather_unit_fast(uc, p.P.align, q.x, q.y, q.z, scene);
+                        } else {
+                            const float *x0b = p.x0 + (int64_t)scene * p.P.D[0] * p.P.H[0] * p.P.W[0];
+                            val = gather_unit_decoded(p.P, 0, 0, 0, q.x, q.y, q.z, x0b, nullptr);
+                        }
                     }
                     *reinterpret_cast<uint4 *>(a_st + swz128(r, unit_in_chunk)) = val;
                     if (p.save_feat) {

@@ -47,7 +47,8 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 template <bool NEED_DPTS>
-__global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict__ points, int N, int64_t total_pts,
+__global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict__ points, const int *__restrict__ perm, int N,
+                                                         int64_t total_pts,
                                                          const float *__restrict__ x0, VolPtrs vols, Pyr P,
                                                          const __nv_bfloat16 *__restrict__ dfeat, float *__restrict__ gx0,
                                                          GradPtrs gv, float *__restrict__ gpoints) {
@@ -55,15 +56,16 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
     const int64_t total = total_pts * UP;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = t < total;
-    int64_t pt = active ? t / UP : total_pts - 1;
-    const int u = active ? (int)(t - pt * UP) : P.n_units;  // inactive -> padding unit
+    const int64_t row = active ? t / UP : total_pts - 1;
+    const int u = active ? (int)(t - row * UP) : P.n_units;  // inactive -> padding unit
+    const int64_t pt = perm ? (int64_t)perm[row] : row;       // dfeat rows are in processing order
     const int b = (int)(pt / N);
     const float px = points[pt * 3 + 0], py = points[pt * 3 + 1], pz = points[pt * 3 + 2];
     float dq[3] = {0.f, 0.f, 0.f};  // d loss / d (x,y,z) sample coordinate, already scaled to normalised units
     int level, d, c0;
     if (decode_unit(P, u, level, d, c0)) {
         float g[8];
-        bf16x8_to_float(*reinterpret_cast<const uint4 *>(dfeat + pt * P.kp + (int64_t)u * 8), g);
+        bf16x8_to_float(*reinterpret_cast<const uint4 *>(dfeat + row * P.kp + (int64_t)u * 8), g);
         if (level == 0) {
             const int64_t base = (int64_t)b * P.D[0] * P.H[0] * P.W[0];
 #pragma unroll
@@ -339,7 +341,7 @@ int svr_gather_fwd(const float *points, int B, int N, const float *x0, const uin
     return 0;
 }
 
-int svr_gather_bwd(const float *points, int B, int N, const float *x0, const uint16_t *const *vols_host,
+int svr_gather_bwd(const float *points, const int *perm, int B, int N, const float *x0, const uint16_t *const *vols_host,
                    const svr_pyramid *pyr_host, const uint16_t *dfeat, float *gx0, float *const *gvols_host, float *gpoints,
                    void *stream) {
     Pyr P;
@@ -357,10 +359,10 @@ int svr_gather_bwd(const float *points, int B, int N, const float *x0, const uin
     int64_t total = total_pts * (P.kp / 8);
     unsigned blocks = (unsigned)ceil_div<int64_t>(total, 256);
     if (gpoints)
-        gather_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(points, N, total_pts, x0, vp, P,
+        gather_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(points, perm, N, total_pts, x0, vp, P,
                                                                        (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints);
     else
-        gather_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(points, N, total_pts, x0, vp, P,
+        gather_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(points, perm, N, total_pts, x0, vp, P,
                                                                         (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints);
     SVR_LAUNCH_CHECK();
     return 0;

@@ -333,7 +333,8 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, int spli
 // small helpers of the decoder backward
 // ------------------------------------------------------------------------------------------------
 // dz2 = dlogit (x) wout masked by h2 > 0;  per-block partials of gwout / gbout
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float *__restrict__ dlogit, const __nv_bfloat16 *__restrict__ h2,
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float *__restrict__ dlogit, const int *__restrict__ perm,
+                                                       const __nv_bfloat16 *__restrict__ h2,
                                                        const float *__restrict__ wout, int M, int Hd,
                                                        __nv_bfloat16 *__restrict__ dz2, float *__restrict__ part_w,
                                                        float *__restrict__ part_b, int rows_per_block) {
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float *__restrict__
     float gw = 0.f, gb = 0.f;
     const float w = col < Hd ? wout[col] : 0.f;
     for (int r = r0; r < r1; ++r) {
-        float dl = dlogit[r];
+        float dl = dlogit[perm ? perm[r] : r];
         if (col < Hd) {
             float h = __bfloat162float(h2[(int64_t)r * Hd + col]);
             gw += dl * h;
@@ -481,8 +482,8 @@ int svr_gemm_tn(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, 
     return 0;
 }
 
-int svr_decoder_head_bwd(const float *dlogit, const uint16_t *h2, const float *wout, int M, int Hd, uint16_t *dz2,
-                         float *gwout, float *gbout, void *stream) {
+int svr_decoder_head_bwd(const float *dlogit, const int *perm, const uint16_t *h2, const float *wout, int M, int Hd,
+                         uint16_t *dz2, float *gwout, float *gbout, void *stream) {
     SVR_REQUIRE(dlogit && h2 && wout && dz2 && gwout && gbout, "decoder_head_bwd: null pointer");
     SVR_REQUIRE(Hd > 0 && Hd <= 256, "decoder_head_bwd: hidden size must be <= 256");
     if (M == 0) return 0;
@@ -491,7 +492,7 @@ int svr_decoder_head_bwd(const float *dlogit, const uint16_t *h2, const float *w
     const int nblocks = ceil_div(M, rows_per_block);
     float *scratch = nullptr;
     if (int rc = scratch_alloc(&scratch, (size_t)nblocks * (Hd + 1), st)) return rc;
-    head_bwd_kernel<<<nblocks, 256, 0, st>>>(dlogit, (const __nv_bfloat16 *)h2, wout, M, Hd, (__nv_bfloat16 *)dz2, scratch,
+    head_bwd_kernel<<<nblocks, 256, 0, st>>>(dlogit, perm, (const __nv_bfloat16 *)h2, wout, M, Hd, (__nv_bfloat16 *)dz2, scratch,
                                              scratch + (size_t)nblocks * Hd, rows_per_block);
     head_bwd_reduce_kernel<<<ceil_div(Hd, 256), 256, 0, st>>>(scratch, scratch + (size_t)nblocks * Hd, nblocks, Hd, gwout, gbout);
     SVR_LAUNCH_CHECK();

@@ -196,6 +196,116 @@ __device__ __forceinline__ uint4 gather_unit(const Pyr &P, int u, float px, floa
     if (!decode_unit(P, u, level, d, c0)) return make_uint4(0, 0, 0, 0);
     return gather_unit_decoded(P, level, d, c0, px, py, pz, x0_b, level > 0 ? vol_b[level] : nullptr);
 }
+// ------------------------------------------------------------------------------------------------
+// Fast path used by the fused kernel: everything that depends only on the UNIT (level geometry,
+// displacement, channel offset, strides) is hoisted into a UnitCtx built once per K-chunk; per point
+// only the index math, 8 vector loads and the blend remain.  The blend uses packed FFMA2
+// (fma.rn.f32x2, sm_100+): two fp32 channels per instruction, fp32 accumulation.
+// ------------------------------------------------------------------------------------------------
+struct UnitCtx {
+    int level, d, c0;
+    bool real;
+    int W, H, D, C;
+    int sy, sz;                  // element strides of y and z steps (W*C, H*W*C)
+    int64_t scene_stride;        // elements per scene
+    float fw, fh, fd;            // sizes as float
+    float dx, dy, dz;            // stencil displacement of this unit (grid_sample x,y,z order)
+    const __nv_bfloat16 *base;   // volume of the level + c0
+};
+
+__device__ __forceinline__ void make_unit_ctx(const Pyr &P, int u, const __nv_bfloat16 *const *vols, UnitCtx &c) {
+    c.real = decode_unit(P, u, c.level, c.d, c.c0);
+    if (!c.real) {
+        c.level = 0;
+        c.d = 0;
+        c.c0 = 0;
+    }
+    const int l = c.level;
+    c.W = P.W[l];
+    c.H = P.H[l];
+    c.D = P.D[l];
+    c.C = P.C[l];
+    c.sy = c.W * c.C;
+    c.sz = c.H * c.sy;
+    c.scene_stride = (int64_t)c.D * c.sz;
+    c.fw = (float)c.W;
+    c.fh = (float)c.H;
+    c.fd = (float)c.D;
+    const float sgn = (c.d & 1) ? -P.delta : P.delta;
+    c.dx = (c.d == 1 || c.d == 2) ? sgn : 0.f;
+    c.dy = (c.d == 3 || c.d == 4) ? sgn : 0.f;
+    c.dz = (c.d == 5 || c.d == 6) ? sgn : 0.f;
+    c.base = l > 0 ? vols[l] + c.c0 : nullptr;
+}
+
+__device__ __forceinline__ float unnorm(float q, float size, int align) {
+    return align ? __fmul_rn(__fmul_rn(__fadd_rn(q, 1.0f), 0.5f), size - 1.0f)
+                 : __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(q, 1.0f), size), 1.0f), 0.5f);
+}
+
+__device__ __forceinline__ void ffma2(unsigned long long &acc, uint32_t packed_bf16x2, float w) {
+    // (lo, hi) bf16 pair -> two fp32 lanes of a 64-bit register; acc += pair * w
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(packed_bf16x2 << 16), "r"(packed_bf16x2 & 0xffff0000u));
+    unsigned long long ww;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(ww));
+}
+
+// one unit (level >= 1) of one point; returns 8 bf16
+__device__ __forceinline__ uint4 gather_unit_fast(const UnitCtx &c, int align, float px, float py, float pz, int scene) {
+    // q = 2*p + displacement: 2*p is exact, so the fused form rounds exactly like the reference's mul + add
+    const float ix = unnorm(__fadd_rn(__fmul_rn(2.0f, pz), c.dx), c.fw, align);
+    const float iy = unnorm(__fadd_rn(__fmul_rn(2.0f, py), c.dy), c.fh, align);
+    const float iz = unnorm(__fadd_rn(__fmul_rn(2.0f, px), c.dz), c.fd, align);
+    float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    fx = fminf(fmaxf(fx, -4.0f), c.fw + 2.0f);
+    fy = fminf(fmaxf(fy, -4.0f), c.fh + 2.0f);
+    fz = fminf(fmaxf(fz, -4.0f), c.fd + 2.0f);
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+    const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+    const float wz1 = iz - fz, wz0 = (fz + 1.0f) - iz;
+    const __nv_bfloat16 *ptr = c.base + (int64_t)scene * c.scene_stride + ((z0 * c.H + y0) * c.W + x0) * c.C;
+    const bool interior = x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + 1 < c.W && y0 + 1 < c.H && z0 + 1 < c.D;
+    uint4 raw[8];
+    float w[8];
+    const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+    if (interior) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int off = ((k & 1) ? c.C : 0) + ((k & 2) ? c.sy : 0) + ((k & 4) ? c.sz : 0);
+            raw[k] = __ldg(reinterpret_cast<const uint4 *>(ptr + off));
+            w[k] = wxy[k & 3] * ((k & 4) ? wz1 : wz0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int x = x0 + (k & 1), y = y0 + ((k >> 1) & 1), z = z0 + (k >> 2);
+            const bool in = x >= 0 && y >= 0 && z >= 0 && x < c.W && y < c.H && z < c.D;
+            const int off = ((k & 1) ? c.C : 0) + ((k & 2) ? c.sy : 0) + ((k & 4) ? c.sz : 0);
+            raw[k] = in ? __ldg(reinterpret_cast<const uint4 *>(ptr + off)) : make_uint4(0, 0, 0, 0);
+            w[k] = in ? wxy[k & 3] * ((k & 4) ? wz1 : wz0) : 0.f;
+        }
+    }
+    unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        ffma2(acc[0], raw[k].x, w[k]);
+        ffma2(acc[1], raw[k].y, w[k]);
+        ffma2(acc[2], raw[k].z, w[k]);
+        ffma2(acc[3], raw[k].w, w[k]);
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        out[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
 #endif  // __CUDACC__
 
 }  // namespace svr

@@ -225,6 +225,17 @@ def _gemm_tn(A, B, M, N, P, out, accumulate=False):
 
 RELU, ST_BF16, ST_F32, MASK, DOT = 1, 2, 4, 8, 16
 USE_FUSED = True     # fused gather+decoder forward kernel when the decoder is 256/256/256
+SORT_MIN_POINTS = 2048   # spatially sort the query points of a scene when it has at least this many
+
+
+def sort_points(pts: torch.Tensor) -> torch.Tensor:
+    """(B,N,3) -> int32 (B*N,) processing order (scene-major, Morton order of 16^3 cells inside a scene)."""
+    B, N, _ = pts.shape
+    perm = torch.empty((B * N,), device=pts.device, dtype=torch.int32)
+    nbytes = _lib().svr_sort_points_workspace_bytes(B, N)
+    ws = torch.empty((nbytes,), device=pts.device, dtype=torch.uint8)
+    _abi.check(_lib().svr_sort_points(pts.data_ptr(), B, N, perm.data_ptr(), ws.data_ptr(), nbytes, _stream()), "sort_points")
+    return perm
 
 
 def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, sigmoid: bool = False, perm=None):
@@ -275,8 +286,11 @@ class _Query(torch.autograd.Function):
         b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
         wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
         needs_bwd = any(ctx.needs_input_grad)
+        perm = None
         if USE_FUSED and "w0p_img" in W:
-            logits, hs, feat = fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save=needs_bwd)
+            if N >= SORT_MIN_POINTS:
+                perm = sort_points(pts)
+            logits, hs, feat = fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save=needs_bwd, perm=perm)
             if not needs_bwd:
                 return logits.view(B, N)
             h0, h1, h2 = hs[0], hs[1], hs[2]
@@ -293,12 +307,14 @@ class _Query(torch.autograd.Function):
         ctx.vol_meta = [(v.shape, v.stride(), ctx.needs_input_grad[12 + i]) for i, v in enumerate(vols)]
         ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[3], ctx.needs_input_grad[2]
         ctx.shapes = (B, N, w0.shape, w1.shape, w2.shape, wo.shape)
-        ctx.save_for_backward(pts, x0, feat, h0, h1, h2, wof, *packed)
+        ctx.has_perm = perm is not None
+        ctx.save_for_backward(pts, x0, feat, h0, h1, h2, wof, perm if perm is not None else pts.new_empty(0), *packed)
         return logits.view(B, N)
 
     @staticmethod
     def backward(ctx, glogits):
-        pts, x0, feat, h0, h1, h2, wof, *packed = ctx.saved_tensors
+        pts, x0, feat, h0, h1, h2, wof, perm, *packed = ctx.saved_tensors
+        perm = perm if ctx.has_perm else None
         pyr, W = ctx.pyr, ctx.cache_t
         B, N, s0, s1, s2, so = ctx.shapes
         M = B * N
@@ -310,8 +326,8 @@ class _Query(torch.autograd.Function):
         dz2 = torch.empty((M, h2n), device=dev, dtype=_BF16)
         gwo = torch.zeros((h2n,), device=dev, dtype=torch.float32)
         gbo = torch.zeros((1,), device=dev, dtype=torch.float32)
-        _abi.check(_lib().svr_decoder_head_bwd(dl.data_ptr(), h2.data_ptr(), wof.data_ptr(), M, h2n, dz2.data_ptr(), gwo.data_ptr(),
-                                               gbo.data_ptr(), st), "decoder_head_bwd")
+        _abi.check(_lib().svr_decoder_head_bwd(dl.data_ptr(), _ptr(perm), h2.data_ptr(), wof.data_ptr(), M, h2n, dz2.data_ptr(),
+                                               gwo.data_ptr(), gbo.data_ptr(), st), "decoder_head_bwd")
 
         def colsum(a, n):
             out = torch.empty((n,), device=dev, dtype=torch.float32)
@@ -350,8 +366,8 @@ class _Query(torch.autograd.Function):
                 gp = torch.zeros_like(pts)
             vt = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
             gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
-            _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
-                                             _ptr(gp), st), "gather_bwd")
+            _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
+                                             _ptr(gx), gt, _ptr(gp), st), "gather_bwd")
             gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
         return (None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
 
@@ -389,7 +405,7 @@ class _Gather(torch.autograd.Function):
         gp = torch.zeros_like(pts) if ctx.p_needs else None
         vt = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
         gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
-        _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
+        _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), None, B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
                                          _ptr(gp), _stream()), "gather_bwd")
         return (None, gp, gx, *[g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs])
 

@@ -30,7 +30,7 @@ wout = torch.randn(Hd).cuda()
 dz2 = torch.empty(M, Hd, device="cuda", dtype=torch.bfloat16)
 gw = torch.zeros(Hd, device="cuda")
 gb = torch.zeros(1, device="cuda")
-_abi.check(lib.svr_decoder_head_bwd(dl.data_ptr(), h2.data_ptr(), wout.data_ptr(), M, Hd, dz2.data_ptr(), gw.data_ptr(), gb.data_ptr(), st))
+_abi.check(lib.svr_decoder_head_bwd(dl.data_ptr(), None, h2.data_ptr(), wout.data_ptr(), M, Hd, dz2.data_ptr(), gw.data_ptr(), gb.data_ptr(), st))
 torch.cuda.synchronize()
 print("head dz2 ", rel(dz2, (dl[:, None] * wout[None]) * (h2.float() > 0)))
 print("head gw  ", rel(gw, (dl[:, None] * h2.float()).sum(0)))

@@ -34,8 +34,9 @@ for (B, N, D) in [(1, 100, 16), (2, 300, 32), (1, 1000, 48), (4, 50000, 128)]:
     l2.sum().backward()
     print("   train-mode logits d", float((l1 - l2).abs().max()), "dpts rel", float((g1 - pr2.grad).norm() / pr2.grad.norm()), flush=True)
 # timing at config-2 shape
-for fused in (False, True):
+for fused, sortmin in ((False, 1 << 30), (True, 1 << 30), (True, 2048)):
     ops.USE_FUSED = fused
+    ops.SORT_MIN_POINTS = sortmin
     with torch.no_grad():
         for _ in range(3):
             net.query(x, vols, pts)
@@ -46,4 +47,4 @@ for fused in (False, True):
             net.query(x, vols, pts)
         e1.record()
         torch.cuda.synchronize()
-    print("fused" if fused else "unfused", "fwd ms (incl. volume + weight packing)", e0.elapsed_time(e1) / 10, flush=True)
+    print("fused" if fused else "unfused", "sorted" if sortmin < 1 << 30 else "unsorted", "fwd ms (incl. volume + weight packing)", e0.elapsed_time(e1) / 10, flush=True)
