@@ -178,8 +178,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _abi.check(_abi.load().svr_device_info(None, None, None, None), "device_info")
 
-    svr_b200.configure(net_res=128)
-    torch.backends.cudnn.benchmark = True       # the reference trainer sets benchmark=True (trainer_ifnet.py:64)
+    svr_b200.configure(net_res=128, channels_last=os.environ.get("SVR_CHANNELS_LAST", "1") == "1")
+    torch.backends.cudnn.benchmark = os.environ.get("SVR_CUDNN_BENCHMARK", "1") == "1"   # reference: trainer_ifnet.py:64
     torch.manual_seed(0)
     net = svr_b200.IFNet().to(dev).train()
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
@@ -246,7 +246,7 @@ def run_ours(args):
         od = occ_pin.to(dev, non_blocking=True)
         return float(step(xd, pd, od).item())       # D2H read of the loss
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
                                                          int64_t total_pts,
                                                          const float *__restrict__ x0, VolPtrs vols, Pyr P,
                                                          const __nv_bfloat16 *__restrict__ dfeat, float *__restrict__ gx0,
-                                                         GradPtrs gv, float *__restrict__ gpoints) {
+                                                         GradPtrs gv, float *__restrict__ gpoints, int red_level_mask) {
     const int UP = P.kp / 8;
     const int64_t total = total_pts * UP;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
     const float px = points[pt * 3 + 0], py = points[pt * 3 + 1], pz = points[pt * 3 + 2];
     float dq[3] = {0.f, 0.f, 0.f};  // d loss / d (x,y,z) sample coordinate, already scaled to normalised units
     int level, d, c0;
-    if (decode_unit(P, u, level, d, c0)) {
+    bool work = decode_unit(P, u, level, d, c0);
+    if (work && !NEED_DPTS && level > 0 && !((red_level_mask >> level) & 1)) work = false;
+    if (work && !NEED_DPTS && level == 0 && !gx0) work = false;
+    if (work) {
         float g[8];
         bf16x8_to_float(*reinterpret_cast<const uint4 *>(dfeat + row * P.kp + (int64_t)u * 8), g);
         if (level == 0) {
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
                 if (!corner_in(P, level, x, y, z)) continue;
                 int64_t off = vbase + (((int64_t)z * P.H[level] + y) * P.W[level] + x) * C;
                 float w = c.wx[aa] * c.wy[bb] * c.wz[e];
-                if (gv.g[level]) {
+                if (gv.g[level] && ((red_level_mask >> level) & 1)) {
                     float *dst = gv.g[level] + off;
                     red_add_v4(dst, g[0] * w, g[1] * w, g[2] * w, g[3] * w);
                     red_add_v4(dst + 4, g[4] * w, g[5] * w, g[6] * w, g[7] * w);
@@ -154,6 +157,218 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
             const int64_t last = __shfl_sync(0xffffffffu, pt, 31);
             if (lane == 0 && va != 0.f) atomicAdd(gpoints + first * 3 + a, va);
             if (lane == 31 && last != first && vb != 0.f) atomicAdd(gpoints + last * 3 + a, vb);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile-aggregated scatter-add for the coarse levels.  Rows arrive spatially sorted (svr_sort_points),
+// so the 128 rows x 7 stencil samples of a tile touch a small box of voxels.  Per tile and level the
+// 7168 (sample, corner) contributions are bucketed by local voxel with a counting sort in shared
+// memory (integer counters only); one thread per (voxel, 8-channel group) then sums its segment in
+// registers and issues ONE pair of 16-byte reductions per tile instead of one per contribution.
+// Tiles whose box exceeds AGG_VMAX voxels (unsorted input, scene boundary) fall back to direct
+// per-contribution reductions for that level.
+// ------------------------------------------------------------------------------------------------
+constexpr int AGG_TILE = 128, AGG_THREADS = 512, AGG_VMAX = 2048, AGG_SAMPLES = AGG_TILE * 7, AGG_CONTRIB = AGG_SAMPLES * 8;
+
+struct AggSmem {
+    float4 pts[AGG_TILE];
+    int box[6];
+    int flags[2];
+    int counts[AGG_VMAX];
+    int start[AGG_VMAX];
+    int cursor[AGG_VMAX];
+    int warp_tot[AGG_THREADS / 32];
+    float w[AGG_CONTRIB];
+    unsigned short sample[AGG_CONTRIB];
+};
+
+__global__ void __launch_bounds__(AGG_THREADS) scatter_agg_kernel(const float *__restrict__ points, const int *__restrict__ perm,
+                                                                  int N, int64_t total_rows, Pyr P,
+                                                                  const __nv_bfloat16 *__restrict__ dfeat, GradPtrs gv,
+                                                                  int level_mask) {
+    extern __shared__ uint8_t agg_raw[];
+    AggSmem &S = *reinterpret_cast<AggSmem *>(agg_raw);
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t row0 = tile * AGG_TILE;
+    if (tid < AGG_TILE) {
+        int64_t row = row0 + tid;
+        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (row < total_rows) {
+            int64_t pt = perm ? (int64_t)perm[row] : row;
+            q = make_float4(points[pt * 3], points[pt * 3 + 1], points[pt * 3 + 2], __int_as_float((int)(pt / N)));
+        }
+        S.pts[tid] = q;
+    }
+    __syncthreads();
+    const int scene0 = __float_as_int(S.pts[0].w);
+
+    for (int level = 1; level < P.n_levels; ++level) {
+        if (!((level_mask >> level) & 1) || !gv.g[level]) continue;   // uniform
+        const int C = P.C[level], W = P.W[level], H = P.H[level], D = P.D[level], ncg = C / 8;
+        // ---- bounding box of the in-bounds corners + single-scene test
+        if (tid < 6) S.box[tid] = (tid < 3) ? 0x7fffffff : -0x7fffffff;
+        if (tid == 6) S.flags[0] = 1;
+        __syncthreads();
+        for (int sidx = tid; sidx < AGG_SAMPLES; sidx += AGG_THREADS) {
+            const int r = sidx / 7, d = sidx - r * 7;
+            const float4 q = S.pts[r];
+            const int scene = __float_as_int(q.w);
+            if (scene < 0) continue;
+            if (scene != scene0) S.flags[0] = 0;
+            Corners c;
+            stencil_corners(P, level, d, q.x, q.y, q.z, c);
+            const int xa = max(c.x0, 0), xb = min(c.x0 + 1, W - 1), ya = max(c.y0, 0), yb = min(c.y0 + 1, H - 1);
+            const int za = max(c.z0, 0), zb = min(c.z0 + 1, D - 1);
+            if (xa <= xb && ya <= yb && za <= zb) {
+                atomicMin(&S.box[0], xa);
+                atomicMin(&S.box[1], ya);
+                atomicMin(&S.box[2], za);
+                atomicMax(&S.box[3], xb);
+                atomicMax(&S.box[4], yb);
+                atomicMax(&S.box[5], zb);
+            }
+        }
+        __syncthreads();
+        const int bx0 = S.box[0], by0 = S.box[1], bz0 = S.box[2];
+        const int nx = S.box[3] - bx0 + 1, ny = S.box[4] - by0 + 1, nz = S.box[5] - bz0 + 1;
+        if (nx <= 0 || ny <= 0 || nz <= 0) {   // nothing in bounds
+            __syncthreads();
+            continue;
+        }
+        const int64_t nvox64 = (int64_t)nx * ny * nz;
+        const bool agg = S.flags[0] && nvox64 <= AGG_VMAX && scene0 >= 0;
+        const int64_t vol_base = (int64_t)scene0 * D * H * W * C;
+        if (agg) {
+            const int nvox = (int)nvox64;
+            for (int i = tid; i < nvox; i += AGG_THREADS) {
+                S.counts[i] = 0;
+                S.cursor[i] = 0;
+            }
+            __syncthreads();
+            // ---- pass 1: count contributions per local voxel
+            for (int sidx = tid; sidx < AGG_SAMPLES; sidx += AGG_THREADS) {
+                const int r = sidx / 7, d = sidx - r * 7;
+                const float4 q = S.pts[r];
+                if (__float_as_int(q.w) < 0) continue;
+                Corners c;
+                stencil_corners(P, level, d, q.x, q.y, q.z, c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int x = c.x0 + (k & 1), y = c.y0 + ((k >> 1) & 1), z = c.z0 + (k >> 2);
+                    if (corner_in(P, level, x, y, z)) atomicAdd(&S.counts[((z - bz0) * ny + (y - by0)) * nx + (x - bx0)], 1);
+                }
+            }
+            __syncthreads();
+            // ---- exclusive scan of counts (<= 2048 entries: 4 per thread)
+            {
+                const int lane = tid & 31, warp = tid >> 5;
+                int v[4], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int i = tid * 4 + j;
+                    v[j] = i < nvox ? S.counts[i] : 0;
+                    sum += v[j];
+                }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) S.warp_tot[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    int wv = lane < AGG_THREADS / 32 ? S.warp_tot[lane] : 0, wi = wv;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int t = __shfl_up_sync(0xffffffffu, wi, o);
+                        if (lane >= o) wi += t;
+                    }
+                    if (lane < AGG_THREADS / 32) S.warp_tot[lane] = wi - wv;
+                }
+                __syncthreads();
+                int run = S.warp_tot[warp] + incl - sum;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int i = tid * 4 + j;
+                    if (i < nvox) S.start[i] = run;
+                    run += v[j];
+                }
+            }
+            __syncthreads();
+            // ---- pass 2: place (sample, weight) into the voxel's segment
+            for (int sidx = tid; sidx < AGG_SAMPLES; sidx += AGG_THREADS) {
+                const int r = sidx / 7, d = sidx - r * 7;
+                const float4 q = S.pts[r];
+                if (__float_as_int(q.w) < 0) continue;
+                Corners c;
+                stencil_corners(P, level, d, q.x, q.y, q.z, c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int aa = k & 1, bb = (k >> 1) & 1, e = k >> 2;
+                    const int x = c.x0 + aa, y = c.y0 + bb, z = c.z0 + e;
+                    if (!corner_in(P, level, x, y, z)) continue;
+                    const int lid = ((z - bz0) * ny + (y - by0)) * nx + (x - bx0);
+                    const int pos = S.start[lid] + atomicAdd(&S.cursor[lid], 1);
+                    S.sample[pos] = (unsigned short)sidx;
+                    S.w[pos] = c.wx[aa] * c.wy[bb] * c.wz[e];
+                }
+            }
+            __syncthreads();
+            // ---- owners: one thread per (voxel, channel group)
+            const int ub = P.ubase[level], upd = P.upd[level];
+            for (int task = tid; task < nvox * ncg; task += AGG_THREADS) {
+                const int vox = task / ncg, cg = task - vox * ncg;
+                const int n = S.counts[vox];
+                if (n == 0) continue;
+                const int s0 = S.start[vox];
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+                for (int i = 0; i < n; ++i) {
+                    const int sidx = S.sample[s0 + i];
+                    const float w = S.w[s0 + i];
+                    const int r = sidx / 7, d = sidx - r * 7;
+                    float g[8];
+                    bf16x8_to_float(__ldg(reinterpret_cast<const uint4 *>(dfeat + (row0 + r) * P.kp + (int64_t)(ub + d * upd + cg) * 8)), g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], w, acc[j]);
+                }
+                const int lx = vox % nx, ly = (vox / nx) % ny, lz = vox / (nx * ny);
+                float *dst = gv.g[level] + vol_base + (((int64_t)(bz0 + lz) * H + (by0 + ly)) * W + (bx0 + lx)) * C + cg * 8;
+                red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+                red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+            }
+            __syncthreads();
+        } else {
+            // ---- fallback: direct reductions, one thread per (row, unit of this level)
+            const int units = 7 * ncg;
+            for (int task = tid; task < AGG_TILE * units; task += AGG_THREADS) {
+                const int r = task / units, uu = task - r * units;
+                const int d = uu / ncg, cg = uu - d * ncg;
+                const float4 q = S.pts[r];
+                const int scene = __float_as_int(q.w);
+                if (scene < 0) continue;
+                float g[8];
+                bf16x8_to_float(__ldg(reinterpret_cast<const uint4 *>(dfeat + (row0 + r) * P.kp + (int64_t)(P.ubase[level] + uu) * 8)), g);
+                Corners c;
+                stencil_corners(P, level, d, q.x, q.y, q.z, c);
+                const int64_t vb = (int64_t)scene * D * H * W * C + cg * 8;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int aa = k & 1, bb = (k >> 1) & 1, e = k >> 2;
+                    const int x = c.x0 + aa, y = c.y0 + bb, z = c.z0 + e;
+                    if (!corner_in(P, level, x, y, z)) continue;
+                    const float w = c.wx[aa] * c.wy[bb] * c.wz[e];
+                    float *dst = gv.g[level] + vb + (((int64_t)z * H + y) * W + x) * C;
+                    red_add_v4(dst, g[0] * w, g[1] * w, g[2] * w, g[3] * w);
+                    red_add_v4(dst + 4, g[4] * w, g[5] * w, g[6] * w, g[7] * w);
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -358,12 +573,33 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
     if (total_pts == 0) return 0;
     int64_t total = total_pts * (P.kp / 8);
     unsigned blocks = (unsigned)ceil_div<int64_t>(total, 256);
-    if (gpoints)
-        gather_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(points, perm, N, total_pts, x0, vp, P,
-                                                                       (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints);
-    else
-        gather_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(points, perm, N, total_pts, x0, vp, P,
-                                                                        (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints);
+    // Levels >= 2 go through the tile-aggregated kernel when the rows are spatially sorted (perm given);
+    // level 1 (finest, < 1 contribution per voxel and tile), level 0 and d(points) stay on the direct kernel.
+    int agg_mask = 0;
+    if (perm && gvols_host)
+        for (int l = 2; l < P.n_levels; ++l)
+            if (gp.g[l]) agg_mask |= 1 << l;
+    const int direct_mask = ~agg_mask;
+    bool direct_needed = gpoints || gx0;
+    for (int l = 1; l < P.n_levels; ++l)
+        if (gp.g[l] && ((direct_mask >> l) & 1)) direct_needed = true;
+    if (direct_needed) {
+        if (gpoints)
+            gather_bwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(points, perm, N, total_pts, x0, vp, P,
+                                                                           (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints, direct_mask);
+        else
+            gather_bwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(points, perm, N, total_pts, x0, vp, P,
+                                                                            (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints, direct_mask);
+    }
+    if (agg_mask) {
+        static bool attr = false;
+        if (!attr) {
+            SVR_CUDA(cudaFuncSetAttribute(scatter_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AggSmem)));
+            attr = true;
+        }
+        scatter_agg_kernel<<<(unsigned)ceil_div<int64_t>(total_pts, AGG_TILE), AGG_THREADS, sizeof(AggSmem), as_stream(stream)>>>(
+            points, perm, N, total_pts, P, (const __nv_bfloat16 *)dfeat, gp, agg_mask);
+    }
     SVR_LAUNCH_CHECK();
     return 0;
 }

@@ -31,6 +31,12 @@ def _load_args():
 
 
 args = _load_args()
+# Run the torch/cuDNN encoder in channels_last_3d (NDHWC): cuDNN's native layout on sm_100 (no
+# nchw<->nhwc transposes around every conv), and the layout the gather / scatter kernels use, so
+# volumes are packed with a plain convert and gradients are handed back without a transpose.
+# Numerically neutral; module signatures and state_dict are unaffected.
+if not hasattr(args, "channels_last"):
+    args.channels_last = True
 
 
 def configure(**kw):
@@ -58,6 +64,15 @@ class _ExtractorBase(nn.Module):
 
     def encode(self, x) -> List[torch.Tensor]:
         raise NotImplementedError
+
+    def _prep(self, x):
+        """Encoder input / weights in channels_last_3d when enabled (see ``args.channels_last``)."""
+        if getattr(args, "channels_last", False) and x.is_cuda:
+            if not self.__dict__.get("_cl_done", False):
+                self.to(memory_format=torch.channels_last_3d)
+                self.__dict__["_cl_done"] = True
+            return x.contiguous(memory_format=torch.channels_last_3d)
+        return x
 
     def pyramid(self, x, vols) -> ops.PyramidSpec:
         chans = [1] + [v.shape[1] for v in vols]
@@ -104,7 +119,7 @@ class IFNetFeatureExtractor(_ExtractorBase):
     def encode(self, x):
         stages = ((self.conv_1, self.conv_1_1, self.conv1_1_bn), (self.conv_2, self.conv_2_1, self.conv2_1_bn),
                   (self.conv_3, self.conv_3_1, self.conv3_1_bn))
-        vols, net = [], x
+        vols, net = [], self._prep(x)
         for i, (ca, cb, bn) in enumerate(stages):
             net = bn(self.actvn(cb(self.actvn(ca(net)))))
             vols.append(net)
@@ -140,7 +155,7 @@ class IFNetFeatureExtractor128(_ExtractorBase):
         self.displacments = _displacements(self.displacement)
 
     def encode(self, x):
-        net = self.conv_in_bn(self.actvn(self.conv_in(x)))
+        net = self.conv_in_bn(self.actvn(self.conv_in(self._prep(x))))
         vols = [net]
         for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
                            (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):

@@ -222,3 +222,39 @@ def test_training_config_shape_properties():
     feat = CO.sample_features([x[0].cpu().numpy()] + [v[0].cpu().numpy() for v in vols], sub[0].cpu().numpy(), R.DISPLACEMENT_128, False)
     ref = CO.decoder(feat, sdn)
     assert np.abs(got[0].numpy() - ref).max() / np.abs(ref).max() < TOL_BF16
+
+
+def test_sorted_aggregated_backward_matches_direct():
+    """The spatially sorted processing order + tile-aggregated scatter (coarse levels) must give the
+    same logits (bit-identical: rows are independent) and the same gradients as the direct path up to
+    fp32 summation order."""
+    import svr_b200
+    ops = svr_b200.ops
+    sd = R.synthetic_state_dict(21, 128)
+    net = _net(128, sd).eval()
+    g = torch.Generator().manual_seed(8)
+    x = (torch.rand((2, 1, 64, 48, 32), generator=g) < 0.1).float().cuda()
+    pts = ((torch.rand((2, 6000, 3), generator=g) - 0.5) * 1.04).cuda()
+    cot = torch.randn((2, 6000), generator=g).cuda()
+    with torch.no_grad():
+        vols = net.ifnet_feature_extractor.encode(x)
+    res = {}
+    old = ops.SORT_MIN_POINTS
+    try:
+        for tag, thr in (("direct", 1 << 30), ("sorted", 1)):
+            ops.SORT_MIN_POINTS = thr
+            net.zero_grad()
+            xx = x.clone().requires_grad_(True)
+            pp = pts.clone().requires_grad_(True)
+            vv = [v.clone().requires_grad_(True) for v in vols]
+            out = net.query(xx, vv, pp)
+            out.backward(cot)
+            res[tag] = (out.detach(), xx.grad, pp.grad, [v.grad for v in vv], net.fc_0.weight.grad.clone(), net.fc_2.bias.grad.clone())
+    finally:
+        ops.SORT_MIN_POINTS = old
+    a, b = res["direct"], res["sorted"]
+    assert torch.equal(a[0], b[0])
+    assert _rel_l2(b[1], a[1]) < 1e-4 and _rel_l2(b[2], a[2]) < 1e-4
+    for va, vb in zip(a[3], b[3]):
+        assert _rel_l2(vb, va) < 1e-4
+    assert _rel_l2(b[4], a[4]) < 1e-4 and _rel_l2(b[5], a[5]) < 1e-4
