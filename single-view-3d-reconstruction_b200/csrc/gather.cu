@@ -403,6 +403,16 @@ __global__ void __launch_bounds__(256) pack_volume_kernel(const float *__restric
     }
 }
 
+// fast path: source already channel-last contiguous -> plain vectorised convert (8 elements/thread)
+__global__ void __launch_bounds__(256) convert_bf16_kernel(const float *__restrict__ src, int64_t n8, __nv_bfloat16 *__restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        reinterpret_cast<uint4 *>(dst)[i] = float8_to_bf16(f);
+    }
+}
+
 // fp32 NDHWC -> (+)= strided fp32 (B,C,D,H,W)
 __global__ void __launch_bounds__(256) unpack_volume_grad_kernel(const float *__restrict__ src, int C, int D, int H, int W,
                                                                  int64_t spatial_total, int64_t sB, int64_t sC, int64_t sD,
@@ -487,6 +497,15 @@ int svr_pack_volume(const float *src, int B, int C, int D, int H, int W, int64_t
     SVR_REQUIRE(C > 0 && C % 2 == 0 && C <= 256, "pack_volume: C must be even and <= 256");
     int64_t spatial = (int64_t)B * D * H * W;
     if (spatial == 0) return 0;
+    const bool ndhwc = sC == 1 && sW == C && sH == (int64_t)W * C && sD == (int64_t)H * W * C && sB == (int64_t)D * H * W * C;
+    if (ndhwc && C % 8 == 0 && ((uintptr_t)src & 15) == 0) {
+        int64_t n8 = spatial * C / 8;
+        int64_t blocks = ceil_div<int64_t>(n8, 256);
+        int64_t cap = (int64_t)sm_count() * 16;
+        convert_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(src, n8, (__nv_bfloat16 *)dst);
+        SVR_LAUNCH_CHECK();
+        return 0;
+    }
     size_t smem = (size_t)C * 33 * sizeof(float);
     pack_volume_kernel<<<(unsigned)ceil_div<int64_t>(spatial, 32), 256, smem, as_stream(stream)>>>(
         src, C, D, H, W, spatial, sB, sC, sD, sH, sW, (__nv_bfloat16 *)dst);

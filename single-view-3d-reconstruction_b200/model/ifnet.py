@@ -199,6 +199,18 @@ class IFNet(nn.Module):
         vols = self.ifnet_feature_extractor.encode(x)
         return self.query(x, vols, points)
 
+    def fused_available(self) -> bool:
+        return self.fc_0.out_channels == 256 and self.fc_1.out_channels == 256 and self.fc_2.out_channels == 256
+
+    @torch.no_grad()
+    def evaluate_grid(self, x, lattice, scenes=None, x_range=None):
+        """Dense occupancy of whole scenes on the (sx,sy,sz) inclusive lattice over [-0.5,0.5]^3:
+        encoder once, then one fused launch per scene.  Returns a CUDA tensor (len(scenes),sx,sy,sz)."""
+        vols = self.ifnet_feature_extractor.encode(x)
+        pyr = self.ifnet_feature_extractor.pyramid(x, vols)
+        return ops.dense_eval(pyr, self._packed, x, vols, self.fc_0.weight, self.fc_0.bias, self.fc_1.weight, self.fc_1.bias,
+                              self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, lattice, scenes, x_range)
+
 
 def make_3d_grid(bb_min, bb_max, shape, res_increase=None):
     """ifnet.py:202-212: inclusive linspace lattice, flattened with the last axis fastest (CPU tensor)."""
@@ -222,6 +234,9 @@ def evaluate_network_on_grid(network, x, resolution, res_increase=None):
     shape = tuple(int(res_increase * int(r)) for r in resolution)
     values = []
     with torch.no_grad():
+        if isinstance(network, IFNet) and not network.training and network.fused_available() and x.is_cuda:
+            # one encoder pass + one fused launch: lattice generated on the fly (no 201 MB point tensor)
+            return network.evaluate_grid(x, shape, scenes=[0])[0].cpu().numpy()
         if isinstance(network, IFNet) and not network.training:
             vols = network.ifnet_feature_extractor.encode(x)
             big = max(points_batch_size, 1 << 20)

@@ -267,6 +267,40 @@ def gather_features(points, x0, packed_vols: List[torch.Tensor], pyr: PyramidSpe
     return feat
 
 
+def _decoder_struct(W, b0f, b1f, b2f, wof, bof):
+    dw = _abi.DecoderWeights()
+    dw.w0p, dw.w1, dw.w2 = W["w0p_img"].data_ptr(), W["w1_img"].data_ptr(), W["w2_img"].data_ptr()
+    dw.b0, dw.b1, dw.b2 = b0f.data_ptr(), b1f.data_ptr(), b2f.data_ptr()
+    dw.wout, dw.bout = wof.data_ptr(), bof.data_ptr()
+    dw.h0 = dw.h1 = dw.h2 = 256
+    return dw
+
+
+def dense_eval(pyr, cache, x, vols, w0, b0, w1, b1, w2, b2, wo, bo, lattice, scenes=None, x_range=None):
+    """sigmoid(decoder(sample(x, make_3d_grid lattice))) for whole scenes in ONE launch per scene
+    (evaluate_network_on_grid, ifnet.py:215-229): the lattice points are generated inside the
+    kernel in brick order, nothing but the (sx,sy,sz) result is written.  Returns (len(scenes), sx, sy, sz).
+    ``x_range=(begin, end)`` restricts the work to a slab of the first lattice axis (point-block
+    sharding across GPUs); the rest of the output is left at zero."""
+    x0 = _dev_f32(x, "x")
+    sx, sy, sz = (int(v) for v in lattice)
+    scenes = list(range(x0.shape[0])) if scenes is None else list(scenes)
+    packed = [pack_volume(v) for v in vols]
+    W = cache.get(pyr, w0, w1, w2)
+    if "w0p_img" not in W:
+        raise RuntimeError("svr_b200: the fused dense evaluator needs a 256/256/256 decoder")
+    b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
+    wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
+    dw = _decoder_struct(W, b0f, b1f, b2f, wof, bof)
+    tbl = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
+    xb, xe = (0, sx) if x_range is None else x_range
+    out = torch.zeros((len(scenes), sx, sy, sz), device=x0.device, dtype=torch.float32)
+    for i, sc in enumerate(scenes):
+        _abi.check(_lib().svr_dense_eval(int(sc), x0.shape[0], x0.data_ptr(), tbl, C.byref(pyr.c), C.byref(dw), sx, sy, sz, int(xb), int(xe),
+                                         out[i].data_ptr(), _stream()), "dense_eval")
+    return out
+
+
 class _Query(torch.autograd.Function):
     """IFNet.forward given the encoder's volumes (ifnet.py:38-61,156-197): stencil gather + decoder.
 

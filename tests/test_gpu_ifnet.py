@@ -258,3 +258,23 @@ def test_sorted_aggregated_backward_matches_direct():
     for va, vb in zip(a[3], b[3]):
         assert _rel_l2(vb, va) < 1e-4
     assert _rel_l2(b[4], a[4]) < 1e-4 and _rel_l2(b[5], a[5]) < 1e-4
+
+
+def test_fused_dense_evaluator_matches_chunked_query():
+    """svr_dense_eval (lattice generated in-kernel, brick order) against the chunked point path on the
+    same make_3d_grid points, incl. non-multiple-of-brick sizes, several scenes and an x-slab."""
+    import svr_b200
+    sd = R.synthetic_state_dict(31, 128)
+    net = _net(128, sd).eval()
+    g = torch.Generator().manual_seed(12)
+    x = (torch.rand((2, 1, 32, 24, 16), generator=g) < 0.15).float().cuda()
+    for lattice in ((19, 10, 7), (32, 24, 16)):
+        dense = net.evaluate_grid(x, lattice)
+        assert dense.shape == (2, *lattice)
+        pts = svr_b200.make_3d_grid((-0.5,) * 3, (0.5,) * 3, lattice, 1).cuda()
+        with torch.no_grad():
+            vols = net.ifnet_feature_extractor.encode(x)
+            ref = torch.sigmoid(net.query(x, vols, pts[None].expand(2, -1, -1).contiguous())).view(2, *lattice)
+        assert float((dense - ref).abs().max()) < 1e-5
+        slab = net.evaluate_grid(x, lattice, scenes=[1], x_range=(8, 16))
+        assert torch.equal(slab[0, 8:16], dense[1, 8:16]) and float(slab[0, :8].abs().max()) == 0.0
