@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace svr {
 using namespace tc;
@@ -26,9 +27,8 @@ constexpr int FQ_NA = 3, FQ_NB = 3;
 constexpr int FQ_A_BYTES = FQ_TILE * 128;        // 16 KB: 128 rows x 64 bf16
 constexpr int FQ_B_BYTES = FQ_HID * 128;         // 32 KB: 256 rows x 64 bf16
 constexpr int FQ_H_BYTES = FQ_TILE * FQ_HID * 2; // 64 KB: 4 K-chunks of 16 KB
-constexpr int FQ_EPI_WARPS = 4, FQ_GATHER_WARPS = 8;
-constexpr int FQ_GATHER_THREADS = FQ_GATHER_WARPS * 32;
-constexpr int FQ_THREADS = (FQ_EPI_WARPS + 2 + FQ_GATHER_WARPS) * 32;   // 448
+constexpr int FQ_EPI_WARPS = 4;
+constexpr int fq_threads(int gather_warps) { return (FQ_EPI_WARPS + 2 + gather_warps) * 32; }   // 448 for 8 gather warps
 constexpr int FQ_SMEM = 1024 + FQ_NA * FQ_A_BYTES + FQ_NB * FQ_B_BYTES + FQ_H_BYTES + 2 * FQ_TILE * 16 + 512;
 
 struct FqVols {
@@ -125,7 +125,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqParams p, int64_t n_tiles) {
+template <int FQ_GATHER_WARPS>
+__global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_kernel(const FqParams p, int64_t n_tiles) {
+    constexpr int FQ_GATHER_THREADS = FQ_GATHER_WARPS * 32;
     extern __shared__ uint8_t smem_raw[];
     const FqSmem s = fq_carve(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,14 +392,22 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
 
 static int fq_launch(const FqParams &p, int64_t n_tiles, cudaStream_t st) {
     static bool attr = false;
+    static int gw = 16;
     if (!attr) {
-        SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
+        SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
+        SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
+        const char *e = getenv("SVR_FQ_GATHER_WARPS");
+        if (e && atoi(e) == 16) gw = 16;
+        if (e && atoi(e) == 8) gw = 8;
         attr = true;
     }
     if (n_tiles <= 0) return 0;
     int grid = sm_count();
     if (n_tiles < grid) grid = (int)n_tiles;
-    fused_query_kernel<<<grid, FQ_THREADS, FQ_SMEM, st>>>(p, n_tiles);
+    if (gw == 16)
+        fused_query_kernel<16><<<grid, fq_threads(16), FQ_SMEM, st>>>(p, n_tiles);
+    else
+        fused_query_kernel<8><<<grid, fq_threads(8), FQ_SMEM, st>>>(p, n_tiles);
     SVR_LAUNCH_CHECK();
     return 0;
 }

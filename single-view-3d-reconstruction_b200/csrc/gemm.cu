@@ -16,12 +16,12 @@
 namespace svr {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, LAG = 2;
+constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int GEMM_THREADS = 288;
 constexpr int NUM_PRODUCERS = 128;
-constexpr size_t GEMM_SMEM = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+constexpr size_t gemm_smem(int stages) { return 1024 + (size_t)stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 256; }
 
 struct GemmNT {
     const __nv_bfloat16 *A, *B;
@@ -49,6 +49,7 @@ struct SmemLayout {
     uint32_t *tmem_ptr;
 };
 
+template <int STAGES>
 __device__ __forceinline__ SmemLayout carve(uint8_t *raw) {
     SmemLayout s;
     uint8_t *base = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -62,6 +63,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t *raw) {
     return s;
 }
 
+template <int STAGES>
 __device__ __forceinline__ uint32_t gemm_prologue(const SmemLayout &s, int warp) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -79,6 +81,7 @@ __device__ __forceinline__ uint32_t gemm_prologue(const SmemLayout &s, int warp)
 }
 
 // producer bookkeeping shared by both kernels: signal stage (kc-LAG) once its copies have landed
+template <int STAGES>
 __device__ __forceinline__ void producer_signal(const SmemLayout &s, int kc_done) {
     fence_proxy_async();
     mbar_arrive(s.full + (kc_done % STAGES));
@@ -87,11 +90,13 @@ __device__ __forceinline__ void producer_signal(const SmemLayout &s, int kc_done
 // ------------------------------------------------------------------------------------------------
 // NT kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmNT p) {
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, (STAGES <= 2 ? 2 : 1)) gemm_nt_kernel(GemmNT p) {
+    constexpr int LAG = STAGES <= 2 ? 1 : 2;
     extern __shared__ uint8_t smem_raw[];
-    const SmemLayout s = carve(smem_raw);
+    const SmemLayout s = carve<STAGES>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem = gemm_prologue(s, warp);
+    const uint32_t tmem = gemm_prologue<STAGES>(s, warp);
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int KC = p.K / BK;
 
@@ -118,11 +123,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmNT p) {
             cp_async_commit();
             if (kc >= LAG) {
                 cp_async_wait<LAG>();
-                producer_signal(s, kc - LAG);
+                producer_signal<STAGES>(s, kc - LAG);
             }
         }
         cp_async_wait<0>();
-        for (int kc = (KC > LAG ? KC - LAG : 0); kc < KC; ++kc) producer_signal(s, kc);
+        for (int kc = (KC > LAG ? KC - LAG : 0); kc < KC; ++kc) producer_signal<STAGES>(s, kc);
     } else if (warp == 4) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
@@ -221,11 +226,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmNT p) {
 // TN kernel: both operands MN-major.  Stage image: 64-element (128 B) column blocks, each holding
 // 64 k-rows of 128 B (8-row swizzle atoms of 1024 B); column blocks are 8192 B apart.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(GemmTN p) {
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, (STAGES <= 2 ? 2 : 1)) gemm_tn_kernel(GemmTN p) {
+    constexpr int LAG = STAGES <= 2 ? 1 : 2;
     extern __shared__ uint8_t smem_raw[];
-    const SmemLayout s = carve(smem_raw);
+    const SmemLayout s = carve<STAGES>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem = gemm_prologue(s, warp);
+    const uint32_t tmem = gemm_prologue<STAGES>(s, warp);
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, split = blockIdx.z;
     const int total_chunks = (p.P + BK - 1) / BK;
     const int kc_begin = split * p.chunks_per_split;
@@ -257,11 +264,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(GemmTN p) {
             cp_async_commit();
             if (kc >= LAG) {
                 cp_async_wait<LAG>();
-                producer_signal(s, kc - LAG);
+                producer_signal<STAGES>(s, kc - LAG);
             }
         }
         cp_async_wait<0>();
-        for (int kc = (KC > LAG ? KC - LAG : 0); kc < KC; ++kc) producer_signal(s, kc);
+        for (int kc = (KC > LAG ? KC - LAG : 0); kc < KC; ++kc) producer_signal<STAGES>(s, kc);
     } else if (warp == 4) {
         if (lane == 0 && KC > 0) {
             const uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
@@ -414,6 +421,16 @@ static int tn_splits(int M, int N, int P) {
     return s;
 }
 
+static int set_gemm_attrs() {
+    static bool done = false;
+    if (done) return 0;
+    SVR_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(2)));
+    SVR_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(4)));
+    SVR_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(4)));
+    done = true;
+    return 0;
+}
+
 // scratch for the head/colsum partials lives in a per-call cudaMallocAsync'd buffer
 static int scratch_alloc(float **ptr, size_t n_floats, cudaStream_t st) {
     SVR_CUDA(cudaMallocAsync((void **)ptr, n_floats * sizeof(float), st));
@@ -439,14 +456,12 @@ int svr_gemm_nt(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, 
     if (M == 0) return 0;
     GemmNT p{(const __nv_bfloat16 *)A, (const __nv_bfloat16 *)B, lda, ldb, ldc, bias, M, N, K, flags,
              (__nv_bfloat16 *)c_bf16, c_f32, (const __nv_bfloat16 *)mask, dot_w, dot_b, out_dot};
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVR_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        SVR_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        attr_set = true;
-    }
+    if (int rc = set_gemm_attrs()) return rc;
     dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
-    gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, as_stream(stream)>>>(p);
+    if (K <= 4 * BK)   // short-K (backward-data) GEMMs: 2 stages -> 2 CTAs/SM, epilogues overlap the next tile's loads
+        gemm_nt_kernel<2><<<grid, GEMM_THREADS, gemm_smem(2), as_stream(stream)>>>(p);
+    else
+        gemm_nt_kernel<4><<<grid, GEMM_THREADS, gemm_smem(4), as_stream(stream)>>>(p);
     SVR_LAUNCH_CHECK();
     return 0;
 }
@@ -462,18 +477,13 @@ int svr_gemm_tn(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, 
     SVR_REQUIRE(M % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: M, N, lda, ldb must be multiples of 8");
     const int splits = tn_splits(M, N, P);
     SVR_REQUIRE(workspace_bytes >= (size_t)splits * M * N * sizeof(float), "gemm_tn: workspace too small");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVR_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        SVR_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        attr_set = true;
-    }
+    if (int rc = set_gemm_attrs()) return rc;
     const int chunks = ceil_div(P, BK);
     GemmTN p{(const __nv_bfloat16 *)A, (const __nv_bfloat16 *)B, lda, ldb, M, N, P, ceil_div(chunks > 0 ? chunks : 1, splits),
              (float *)workspace};
     dim3 grid(ceil_div(M, BM), ceil_div(N, BN), splits);
     cudaStream_t st = as_stream(stream);
-    gemm_tn_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
+    gemm_tn_kernel<4><<<grid, GEMM_THREADS, gemm_smem(4), st>>>(p);
     SVR_LAUNCH_CHECK();
     int64_t MN = (int64_t)M * N;
     splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, st>>>((const float *)workspace, splits, MN, N, C, ldc,
