@@ -433,6 +433,18 @@ static int set_gemm_attrs() {
 
 // scratch for the head/colsum partials lives in a per-call cudaMallocAsync'd buffer
 static int scratch_alloc(float **ptr, size_t n_floats, cudaStream_t st) {
+    // keep freed scratch in the stream-ordered pool: with the default release threshold (0) the pool
+    // returns memory to the OS at every synchronisation and the next allocation re-maps it (milliseconds)
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    SVR_CUDA(cudaGetDevice(&dev));
+    if (dev != pool_dev) {
+        cudaMemPool_t pool;
+        SVR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = ~0ull;
+        SVR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_dev = dev;
+    }
     SVR_CUDA(cudaMallocAsync((void **)ptr, n_floats * sizeof(float), st));
     return 0;
 }

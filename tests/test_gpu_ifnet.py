@@ -225,9 +225,10 @@ def test_training_config_shape_properties():
 
 
 def test_sorted_aggregated_backward_matches_direct():
-    """The spatially sorted processing order + tile-aggregated scatter (coarse levels) must give the
-    same logits (bit-identical: rows are independent) and the same gradients as the direct path up to
-    fp32 summation order."""
+    """The spatially sorted processing order + tensor-core scatter (coarse levels) must give the same
+    logits (bit-identical: rows are independent) and the same gradients as the direct path: weights and
+    point/grid gradients up to fp32 summation order (1e-4), coarse-level volume gradients to 5e-3
+    relative L2 (the tensor-core scatter carries the trilinear weights in bf16)."""
     import svr_b200
     ops = svr_b200.ops
     sd = R.synthetic_state_dict(21, 128)
@@ -256,7 +257,7 @@ def test_sorted_aggregated_backward_matches_direct():
     assert torch.equal(a[0], b[0])
     assert _rel_l2(b[1], a[1]) < 1e-4 and _rel_l2(b[2], a[2]) < 1e-4
     for va, vb in zip(a[3], b[3]):
-        assert _rel_l2(vb, va) < 1e-4
+        assert _rel_l2(vb, va) < 5e-3
     assert _rel_l2(b[4], a[4]) < 1e-4 and _rel_l2(b[5], a[5]) < 1e-4
 
 

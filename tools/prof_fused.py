@@ -21,8 +21,7 @@ if mode == "fwd":
             out = net.query(x, vols, pts)
 else:
     for _ in range(3):
-        pr = pts.clone().requires_grad_(True)
-        out = net.query(x, [v.clone().requires_grad_(True) for v in vols], pr)
+        out = net.query(x, [v.clone().requires_grad_(True) for v in vols], pts)
         out.sum().backward()
 torch.cuda.synchronize()
 print("ok", float(out.sum()))
