@@ -135,6 +135,13 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
                    const uint16_t *const *vols_host, const svr_pyramid *pyr_host, const uint16_t *dfeat,
                    float *gx0, float *const *gvols_host, float *gpoints, void *stream);
 
+/* nn.MaxPool3d(2) of the encoder (ifnet.py:133,169-190) on channels-last (NDHWC) fp32 activations,
+ * forward (+ packed per-channel argmax, one byte per output element, 4 per uint32) and backward.
+ * Keeps the torch/cuDNN encoder channels-last end to end (torch's max_pool3d would make an NCDHW
+ * copy).  torch semantics: floor output size, first maximum wins, NaN propagates.  C %% 4 == 0.  */
+int svr_maxpool2_cl_fwd(const float *in, int B, int D, int H, int W, int C, float *out, uint32_t *idx, void *stream);
+int svr_maxpool2_cl_bwd(const float *gout, const uint32_t *idx, int B, int D, int H, int W, int C, float *gin, void *stream);
+
 /* Processing order for the query kernels: perm (B*N ints) lists point indices sorted by (scene,
  * Morton code of a 16^3 cell), so that consecutive rows are spatial neighbours (cache locality of
  * the gather; the reference has no counterpart -- every row is independent, results do not change).*/

@@ -65,6 +65,13 @@ class _ExtractorBase(nn.Module):
     def encode(self, x) -> List[torch.Tensor]:
         raise NotImplementedError
 
+    def _pool(self, net):
+        """nn.MaxPool3d(2): channels-last kernel when the activation is channels-last fp32, else torch's."""
+        if (getattr(args, "channels_last", False) and net.is_cuda and net.dtype == torch.float32 and net.shape[1] % 4 == 0
+                and net.is_contiguous(memory_format=torch.channels_last_3d) and min(net.shape[2:]) >= 2):
+            return ops.maxpool2_channels_last(net)
+        return self.maxpool(net)
+
     def _prep(self, x):
         """Encoder input / weights in channels_last_3d when enabled (see ``args.channels_last``)."""
         if getattr(args, "channels_last", False) and x.is_cuda:
@@ -124,7 +131,7 @@ class IFNetFeatureExtractor(_ExtractorBase):
             net = bn(self.actvn(cb(self.actvn(ca(net)))))
             vols.append(net)
             if i + 1 < len(stages):
-                net = self.maxpool(net)
+                net = self._pool(net)
         return vols
 
 
@@ -159,7 +166,7 @@ class IFNetFeatureExtractor128(_ExtractorBase):
         vols = [net]
         for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
                            (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):
-            net = self.maxpool(net)
+            net = self._pool(net)
             net = bn(self.actvn(cb(self.actvn(ca(net)))))
             vols.append(net)
         return vols

@@ -144,6 +144,41 @@ def blur(grid, taps_w, taps_h, taps_d):
 
 
 # =================================================================================================
+# encoder helper: channels-last 2x2x2 max pooling
+# =================================================================================================
+class _MaxPool2CL(torch.autograd.Function):
+    """nn.MaxPool3d(2) on a channels_last_3d activation without leaving NDHWC."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, Cc, D, H, W = x.shape
+        xp = x.permute(0, 2, 3, 4, 1)                      # NDHWC view of the channels-last tensor
+        if not xp.is_contiguous():
+            xp = xp.contiguous()
+        out = torch.empty((B, D // 2, H // 2, W // 2, Cc), device=x.device, dtype=torch.float32)
+        idx = torch.empty((out.numel() // 4,), device=x.device, dtype=torch.int32)
+        _abi.check(_lib().svr_maxpool2_cl_fwd(xp.data_ptr(), B, D, H, W, Cc, out.data_ptr(), idx.data_ptr(), _stream()), "maxpool_fwd")
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, Cc, D, H, W)
+        return out.permute(0, 4, 1, 2, 3)                  # logical NCDHW, physically channels-last
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        B, Cc, D, H, W = ctx.shape
+        g = gout.permute(0, 2, 3, 4, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        gin = torch.empty((B, D, H, W, Cc), device=gout.device, dtype=torch.float32)
+        _abi.check(_lib().svr_maxpool2_cl_bwd(g.data_ptr(), idx.data_ptr(), B, D, H, W, Cc, gin.data_ptr(), _stream()), "maxpool_bwd")
+        return gin.permute(0, 4, 1, 2, 3)
+
+
+def maxpool2_channels_last(x: torch.Tensor) -> torch.Tensor:
+    return _MaxPool2CL.apply(x)
+
+
+# =================================================================================================
 # IF-Net sampling + decoder
 # =================================================================================================
 class PyramidSpec:

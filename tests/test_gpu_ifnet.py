@@ -279,3 +279,20 @@ def test_fused_dense_evaluator_matches_chunked_query():
         assert float((dense - ref).abs().max()) < 1e-5
         slab = net.evaluate_grid(x, lattice, scenes=[1], x_range=(8, 16))
         assert torch.equal(slab[0, 8:16], dense[1, 8:16]) and float(slab[0, :8].abs().max()) == 0.0
+
+
+def test_channels_last_maxpool_matches_torch():
+    import svr_b200
+    g = torch.Generator().manual_seed(3)
+    for shape in ((2, 16, 8, 6, 10), (1, 32, 9, 7, 5), (2, 128, 2, 2, 2)):
+        x = torch.randn(shape, generator=g).cuda()
+        x[0, :, :2, :2, :2] = 0.25                      # ties: the first maximum must win, like torch
+        xa = x.clone().contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+        xb = x.clone().requires_grad_(True)
+        ya = svr_b200.ops.maxpool2_channels_last(xa)
+        yb = torch.nn.functional.max_pool3d(xb, 2)
+        assert torch.equal(ya, yb) and ya.is_contiguous(memory_format=torch.channels_last_3d)
+        cot = torch.randn(yb.shape, generator=g).cuda()
+        ya.backward(cot)
+        yb.backward(cot)
+        assert torch.equal(xa.grad, xb.grad)
