@@ -135,6 +135,14 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
                    const uint16_t *const *vols_host, const svr_pyramid *pyr_host, const uint16_t *dfeat,
                    float *gx0, float *const *gvols_host, float *gpoints, void *stream);
 
+/* First encoder layer fused with its ReLU: relu(Conv3d(1 -> Co, 3x3x3, padding 1)(x)) (ifnet.py:126,164;
+ * 32-net :68,100).  x (B,D,H,W) fp32, w (Co,27) = conv.weight, y (B,D,H,W,Co) fp32 NDHWC.  Co in {16,32}.
+ * Backward: gw (Co,27), gb (Co), optional gx (B,D,H,W) from gy (NDHWC) and the saved output y.      */
+int svr_conv1_relu_fwd(const float *x, const float *w, const float *bias, int B, int D, int H, int W, int Co, float *y, void *stream);
+size_t svr_conv1_relu_bwd_workspace_bytes(int Co);
+int svr_conv1_relu_bwd(const float *x, const float *y, const float *gy, const float *w, int B, int D, int H, int W, int Co,
+                       float *gw, float *gb, float *gx, void *workspace, size_t workspace_bytes, void *stream);
+
 /* nn.MaxPool3d(2) of the encoder (ifnet.py:133,169-190) on channels-last (NDHWC) fp32 activations,
  * forward (+ packed per-channel argmax, one byte per output element, 4 per uint32) and backward.
  * Keeps the torch/cuDNN encoder channels-last end to end (torch's max_pool3d would make an NCDHW

@@ -174,6 +174,45 @@ class _MaxPool2CL(torch.autograd.Function):
         return gin.permute(0, 4, 1, 2, 3)
 
 
+class _Conv1ReLU(torch.autograd.Function):
+    """relu(Conv3d(1 -> Co, 3, padding=1)(x)) with a channels-last output (first encoder layer)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x0 = _dev_f32(x, "x")
+        B, _, D, H, W = x0.shape
+        Co = weight.shape[0]
+        w = _dev_f32(weight.detach().reshape(Co, 27), "weight")
+        b = _dev_f32(bias.detach(), "bias") if bias is not None else None
+        y = torch.empty((B, D, H, W, Co), device=x0.device, dtype=torch.float32)
+        _abi.check(_lib().svr_conv1_relu_fwd(x0.data_ptr(), w.data_ptr(), _ptr(b), B, D, H, W, Co, y.data_ptr(), _stream()), "conv1_relu_fwd")
+        ctx.save_for_backward(x0, y, w)
+        ctx.has_bias = bias is not None
+        ctx.wshape = weight.shape
+        return y.permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x0, y, w = ctx.saved_tensors
+        B, _, D, H, W = x0.shape
+        Co = w.shape[0]
+        g = gy.permute(0, 2, 3, 4, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        gw = torch.empty((Co, 27), device=x0.device, dtype=torch.float32)
+        gb = torch.empty((Co,), device=x0.device, dtype=torch.float32)
+        gx = torch.empty_like(x0) if ctx.needs_input_grad[0] else None
+        nbytes = _lib().svr_conv1_relu_bwd_workspace_bytes(Co)
+        ws = torch.empty((nbytes,), device=x0.device, dtype=torch.uint8)
+        _abi.check(_lib().svr_conv1_relu_bwd(x0.data_ptr(), y.data_ptr(), g.data_ptr(), w.data_ptr(), B, D, H, W, Co, gw.data_ptr(),
+                                             gb.data_ptr(), _ptr(gx), ws.data_ptr(), nbytes, _stream()), "conv1_relu_bwd")
+        return gx, gw.view(ctx.wshape), (gb if ctx.has_bias else None)
+
+
+def conv1_relu_channels_last(x, weight, bias):
+    return _Conv1ReLU.apply(x, weight, bias)
+
+
 def maxpool2_channels_last(x: torch.Tensor) -> torch.Tensor:
     return _MaxPool2CL.apply(x)
 

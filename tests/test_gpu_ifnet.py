@@ -296,3 +296,29 @@ def test_channels_last_maxpool_matches_torch():
         ya.backward(cot)
         yb.backward(cot)
         assert torch.equal(xa.grad, xb.grad)
+
+
+@pytest.mark.parametrize("co", [16, 32])
+def test_first_conv_relu_matches_torch(co):
+    """csrc/conv_in.cu against F.conv3d + relu in fp32 (TF32 disabled for the comparison)."""
+    import svr_b200
+    g = torch.Generator().manual_seed(co)
+    x = torch.rand((2, 1, 9, 12, 10), generator=g).cuda()
+    w = (torch.randn((co, 1, 3, 3, 3), generator=g) * 0.3).cuda()
+    b = (torch.randn((co,), generator=g) * 0.1).cuda()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xa, wa, ba = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        xb, wb, bb = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ya = svr_b200.ops.conv1_relu_channels_last(xa, wa, ba)
+        yb = torch.relu(torch.nn.functional.conv3d(xb, wb, bb, padding=1))
+        assert ya.is_contiguous(memory_format=torch.channels_last_3d)
+        assert float((ya - yb).abs().max()) < 1e-5
+        cot = torch.randn(yb.shape, generator=g).cuda()
+        ya.backward(cot)
+        yb.backward(cot)
+        for p, q in ((xa, xb), (wa, wb), (ba, bb)):
+            assert float((p.grad - q.grad).abs().max() / q.grad.abs().max()) < 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

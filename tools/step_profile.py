@@ -28,7 +28,15 @@ def step():
 for _ in range(4):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=False) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
     step()
     torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+
+
+evs = sorted([e for e in prof.events() if e.device_type.name == "CPU"], key=lambda e: e.time_range.start)
+for i, ev in enumerate(evs):
+    if ev.name == "aten::to" and ev.input_shapes and ev.input_shapes[0] == [4, 16, 128, 128, 128]:
+        for e in evs[max(0, i - 25):i + 6]:
+            print("   ", e.time_range.start, e.name, e.input_shapes[:2] if e.input_shapes else "")
+        break
