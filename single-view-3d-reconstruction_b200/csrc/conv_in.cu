@@ -49,41 +49,42 @@ __global__ void __launch_bounds__(256) conv1_relu_fwd_kernel(const float *__rest
     }
 }
 
-// weight/bias gradient partials.  Each block walks a contiguous chunk of voxels in tiles of 128:
-// the masked gradient gz = gy * [y > 0] (128 x CO) and the 27 shifted copies of x (27 x 128, plus a row
-// of ones for the bias) are staged in shared memory with coalesced loads, then thread (tap, channel
-// quad) accumulates its 4 weights over the tile from shared memory only.
+// weight/bias gradient partials.  Work unit = one x-row segment of up to 128 voxels.  Per segment the
+// masked gradient gz = gy * [y > 0] (128 x CO) and the 3x3 neighbouring x-rows (with a 1-voxel halo)
+// are staged in shared memory with coalesced loads; thread (tap, channel quad) then accumulates its 4
+// weights over the segment from shared memory only.  Tap 27 is the bias row (x == 1).
 constexpr int C1_TV = 128;
 
 template <int CO>
 __global__ void __launch_bounds__(256) conv1_relu_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ y,
-                                                               const float *__restrict__ gy, int D, int H, int W, int64_t n_vox,
-                                                               int64_t vox_per_block, float *__restrict__ partial) {
+                                                               const float *__restrict__ gy, int B, int D, int H, int W,
+                                                               int64_t n_seg, int64_t seg_per_block, float *__restrict__ partial) {
     constexpr int CQ = CO / 4;
     constexpr int NT = 28 * CQ;                 // (tap, channel quad) workers: 112 (CO=16) / 224 (CO=32)
     constexpr int SETS = 256 / NT;              // voxel sub-ranges processed concurrently: 2 / 1
     __shared__ float4 gz_s[C1_TV][CQ];
-    __shared__ float xs[28][C1_TV];
+    __shared__ float halo[9][C1_TV + 2];        // rows (dz,dy) in {-1,0,1}^2, columns x0-1 .. x0+nv
     __shared__ float4 red[256];
-    __shared__ int cz[C1_TV], cy[C1_TV], cx[C1_TV];
     const int tid = threadIdx.x;
     const int set = tid / NT, t = tid - set * NT;
     const bool worker = set < SETS;
     const int tap = worker ? t / CQ : 0, cq = worker ? t - (t / CQ) * CQ : 0;
-    const int64_t p0 = (int64_t)blockIdx.x * vox_per_block;
-    int64_t p1 = p0 + vox_per_block;
-    if (p1 > n_vox) p1 = n_vox;
+    const int trow = tap < 27 ? tap / 3 : 0, tdx = tap < 27 ? tap % 3 : 0;
+    const int segs_per_row = (W + C1_TV - 1) / C1_TV;
+    const int64_t s0 = (int64_t)blockIdx.x * seg_per_block;
+    int64_t s1 = s0 + seg_per_block;
+    if (s1 > n_seg) s1 = n_seg;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t base = p0; base < p1; base += C1_TV) {
-        const int nv = (int)((p1 - base) < C1_TV ? (p1 - base) : C1_TV);
-        if (tid < C1_TV) {   // voxel coordinates once per tile (the only 64-bit div/mod)
-            const int64_t p = base + tid;
-            cx[tid] = (int)(p % W);
-            cy[tid] = (int)((p / W) % H);
-            cz[tid] = (int)((p / ((int64_t)W * H)) % D);
-        }
-        // stage gz
-        for (int i = tid; i < C1_TV * CQ; i += 256) {
+    for (int64_t sg = s0; sg < s1; ++sg) {
+        const int xs0 = (int)(sg % segs_per_row) * C1_TV;
+        int64_t r = sg / segs_per_row;                       // row index over (b, z, y)
+        const int yy = (int)(r % H);
+        r /= H;
+        const int zz = (int)(r % D);
+        const int64_t b = r / D;
+        const int nv = (W - xs0) < C1_TV ? (W - xs0) : C1_TV;
+        const int64_t base = ((b * D + zz) * H + yy) * (int64_t)W + xs0;
+        for (int i = tid; i < C1_TV * CQ; i += 256) {        // stage gz
             const int v = i / CQ, c = i - v * CQ;
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (v < nv) {
@@ -96,29 +97,23 @@ __global__ void __launch_bounds__(256) conv1_relu_wgrad_kernel(const float *__re
             }
             gz_s[v][c] = g;
         }
-        __syncthreads();
-        // stage the 27 shifted copies of x (+ ones)
-        for (int i = tid; i < 28 * C1_TV; i += 256) {
-            const int tp = i / C1_TV, v = i - tp * C1_TV;
+        for (int i = tid; i < 9 * (C1_TV + 2); i += 256) {   // stage the 3x3 rows with halo
+            const int row = i / (C1_TV + 2), col = i - row * (C1_TV + 2);
+            const int z = zz + row / 3 - 1, yq = yy + row % 3 - 1, xq = xs0 + col - 1;
             float val = 0.f;
-            if (v < nv) {
-                if (tp == 27) {
-                    val = 1.f;
-                } else {
-                    const int dz = tp / 9 - 1, dy = (tp / 3) % 3 - 1, dx = tp % 3 - 1;
-                    const int z = cz[v] + dz, yq = cy[v] + dy, xq = cx[v] + dx;
-                    if (z >= 0 && z < D && yq >= 0 && yq < H && xq >= 0 && xq < W) val = __ldg(x + base + v + (dz * H + dy) * W + dx);
-                }
-            }
-            xs[tp][v] = val;
+            if (col < nv + 2 && z >= 0 && z < D && yq >= 0 && yq < H && xq >= 0 && xq < W)
+                val = __ldg(x + ((b * D + z) * H + yq) * (int64_t)W + xq);
+            halo[row][col] = val;
         }
         __syncthreads();
         if (worker) {
-            const int v0 = set * (C1_TV / SETS), v1 = v0 + C1_TV / SETS;
+            const int v0 = set * (C1_TV / SETS);
+            int v1 = v0 + C1_TV / SETS;
+            if (v1 > nv) v1 = nv;
 #pragma unroll 4
             for (int v = v0; v < v1; ++v) {
                 const float4 g = gz_s[v][cq];
-                const float xv = xs[tap][v];
+                const float xv = tap < 27 ? halo[trow][v + tdx] : 1.f;
                 acc.x = fmaf(g.x, xv, acc.x);
                 acc.y = fmaf(g.y, xv, acc.y);
                 acc.z = fmaf(g.z, xv, acc.z);
@@ -133,8 +128,8 @@ __global__ void __launch_bounds__(256) conv1_relu_wgrad_kernel(const float *__re
         float4 o = acc;
 #pragma unroll
         for (int s2 = 1; s2 < SETS; ++s2) {
-            const float4 r = red[s2 * NT + t];
-            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            const float4 rr = red[s2 * NT + t];
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
         }
         reinterpret_cast<float4 *>(partial + (int64_t)blockIdx.x * 28 * CO + tap * CO)[cq] = o;   // partial[block][tap][co]
     }
@@ -193,8 +188,9 @@ template <int CO>
 static int conv1_bwd_impl(const float *x, const float *y, const float *gy, const float *w, int B, int D, int H, int W, float *gw,
                           float *gb, float *gx, float *partial, int nblocks, cudaStream_t st) {
     const int64_t n_vox = (int64_t)B * D * H * W;
-    const int64_t per_block = ceil_div<int64_t>(n_vox, nblocks);
-    conv1_relu_wgrad_kernel<CO><<<nblocks, 256, 0, st>>>(x, y, gy, D, H, W, n_vox, per_block, partial);
+    const int64_t n_seg = (int64_t)B * D * H * ceil_div(W, C1_TV);
+    const int64_t per_block = ceil_div<int64_t>(n_seg, nblocks);
+    conv1_relu_wgrad_kernel<CO><<<nblocks, 256, 0, st>>>(x, y, gy, B, D, H, W, n_seg, per_block, partial);
     conv1_wgrad_reduce_kernel<<<ceil_div(28 * CO, 128), 128, 0, st>>>(partial, nblocks, CO, gw, gb);
     if (gx) {
         int64_t blocks = ceil_div<int64_t>(n_vox, 256);
