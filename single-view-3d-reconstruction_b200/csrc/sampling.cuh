@@ -6,7 +6,10 @@
 // channels so that one unit == one contiguous channel-last load per corner:
 //   unit 0            : level 0 (1 channel): the 7 stencil samples d=0..6, then one zero
 //   units of level l  : for d in 0..6, for g in 0..C_l/8-1 : channels g*8..g*8+7 of stencil point d
-//   padding units     : zeros up to KP = 64 * ceil(units/8)
+//   padding units     : zeros (a) before every level whose channel count is a multiple of 64, up to the
+//                       next multiple of 8 units, so that each (level, stencil point) block of such a level
+//                       is a whole number of 64-wide K chunks (the tensor-core gather produces whole chunks),
+//                       and (b) at the end up to KP = 64 * ceil(units/8)
 // fc_0's weight is permuted to the same order once per weight update (svr_pack_w0).
 #pragma once
 #include "common.cuh"
@@ -45,6 +48,7 @@ static inline int make_pyr(Pyr &P, const svr_pyramid *h) {
             P.ubase[0] = 0;
         } else {
             P.upd[l] = h->channels[l] / 8;
+            if (h->channels[l] % 64 == 0) u = ((u + 7) / 8) * 8;   // chunk-align coarse (wide) levels
             P.ubase[l] = u;
             u += 7 * P.upd[l];
         }
@@ -68,6 +72,7 @@ __device__ __forceinline__ bool decode_unit(const Pyr &P, int u, int &level, int
     for (int l = 1; l < SVR_MAX_LEVELS; ++l)
         if (l < P.n_levels && u >= P.ubase[l]) level = l;
     int t = u - P.ubase[level];
+    if (t >= (level == 0 ? 1 : 7 * P.upd[level])) return false;   // alignment padding between levels
     d = t / P.upd[level];
     c0 = (t - d * P.upd[level]) * 8;
     return true;

@@ -533,6 +533,8 @@ def feature_index_map(pyr: PyramidSpec, device) -> torch.Tensor:
     coff = 1
     for l in range(1, len(pyr.channels)):
         upd = pyr.channels[l] // 8
+        if pyr.channels[l] % 64 == 0:
+            ubase = (ubase + 7) // 8 * 8          # same chunk alignment as csrc/sampling.cuh make_pyr
         for d in range(7):
             for cc in range(pyr.channels[l]):
                 cols[(coff + cc, d)] = (ubase + d * upd + cc // 8) * 8 + cc % 8
