@@ -70,6 +70,7 @@ _SIGS = {
                               C.c_size_t, vp]),
     "svr_decoder_head_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "svr_colsum_bf16": (C.c_int, [vp, C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp]),
+    "svr_debug_fq_modes": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "svr_pack_decoder_image": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "svr_query_fwd_fused": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), C.POINTER(DecoderWeights),
                                       vp, vp, vp, C.c_int, vp]),

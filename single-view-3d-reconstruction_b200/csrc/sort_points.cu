@@ -1,4 +1,4 @@
-// Spatial ordering of query points: a counting sort on (scene, Morton code of a coarse 16^3 cell).
+// Spatial ordering of query points: a counting sort on (scene, Morton code of a 16^3 cell).
 // Consecutive rows of the fused query kernel then touch neighbouring voxels, so the corner fetches
 // of the coarse feature levels (87 % of the gathered bytes) hit in L1 instead of going to L2.
 // The order inside a cell is irrelevant (every row is independent); only integer counters are used.
@@ -9,10 +9,11 @@ namespace svr {
 constexpr int SORT_CELLS = 16;                                  // per axis
 constexpr int SORT_KEYS = SORT_CELLS * SORT_CELLS * SORT_CELLS;   // per scene
 
-__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // 4 bits -> every third bit
-    v &= 0xF;
-    v = (v | (v << 4)) & 0xC3;
-    v = (v | (v << 2)) & 0x249;
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // up to 5 bits -> every third bit
+    v &= 0x1F;
+    v = (v | (v << 8)) & 0x100F;
+    v = (v | (v << 4)) & 0x10C3;
+    v = (v | (v << 2)) & 0x1249;
     return v;
 }
 
