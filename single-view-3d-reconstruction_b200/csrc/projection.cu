@@ -333,6 +333,212 @@ __global__ void conv_axis_kernel(const float *__restrict__ in, float *__restrict
     out[i] = acc;
 }
 
+// Fused separable blur: ONE pass over the grid.  A block owns a (16 x 64) column of (y, x) and marches
+// along z: every input plane (plus its y/x halo) is loaded once, the W and H correlations run in shared
+// memory, the result enters a ring of kd planes, and the D correlation + clamp is emitted as soon as the
+// ring holds the needed planes: 4 B read + 4 B written per voxel instead of three read+write passes.
+// Out-of-grid input is zero, which reproduces the zero padding of every stage (the reference's order
+// W, then H, then D -- projection.py:110-114).
+constexpr int BL_TY = 16, BL_TX = 64, BL_MAXR = 3, BL_MAXK = 2 * BL_MAXR + 1;
+
+__global__ void __launch_bounds__(256) blur_fused_kernel(const float *__restrict__ in, float *__restrict__ out, int D, int H, int W,
+                                                         const float *__restrict__ taps_w, int kw, const float *__restrict__ taps_h, int kh,
+                                                         const float *__restrict__ taps_d, int kd) {
+    constexpr int EY = BL_TY + 2 * BL_MAXR, EX = BL_TX + 2 * BL_MAXR;
+    constexpr int NLOAD = (EY * EX + 255) / 256;       // halo-plane elements per thread (upper bound)
+    constexpr int NW = (EY * BL_TX + 255) / 256;       // W-pass elements per thread
+    constexpr int NO = (BL_TY * BL_TX) / 256;          // output elements per thread
+    __shared__ float s_in[EY * EX];
+    __shared__ float s_w[EY * BL_TX];
+    __shared__ float ring[BL_MAXK][BL_TY * BL_TX];
+    __shared__ float tw[BL_MAXK], th[BL_MAXK], td[BL_MAXK];
+    const int rw = kw / 2, rh = kh / 2, rd = kd / 2;
+    const int ey = BL_TY + 2 * rh, ex = BL_TX + 2 * rw;
+    if (threadIdx.x < kw) tw[threadIdx.x] = taps_w[threadIdx.x];
+    if (threadIdx.x < kh) th[threadIdx.x] = taps_h[threadIdx.x];
+    if (threadIdx.x < kd) td[threadIdx.x] = taps_d[threadIdx.x];
+    const int tiles_x = (W + BL_TX - 1) / BL_TX, tiles_y = (H + BL_TY - 1) / BL_TY;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int64_t b = t / tiles_y;
+    const int x0 = tx * BL_TX, y0 = ty * BL_TY;
+    const float *src = in + b * (int64_t)D * H * W;
+    float *dst = out + b * (int64_t)D * H * W;
+    const int64_t plane_stride = (int64_t)H * W;
+    // per-thread constant addressing (computed once, reused for every plane)
+    int ld_off[NLOAD];       // offset inside a plane, or -1 (outside the grid / unused slot)
+#pragma unroll
+    for (int j = 0; j < NLOAD; ++j) {
+        const int i = threadIdx.x + j * 256;
+        ld_off[j] = -1;
+        if (i < ey * ex) {
+            const int lx = i % ex, ly = i / ex;
+            const int x = x0 + lx - rw, y = y0 + ly - rh;
+            if (x >= 0 && x < W && y >= 0 && y < H) ld_off[j] = y * W + x;
+        }
+    }
+    int st_off[NO];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+        const int i = threadIdx.x + j * 256;
+        const int lx = i % BL_TX, ly = i / BL_TX;
+        st_off[j] = (x0 + lx < W && y0 + ly < H) ? (y0 + ly) * W + x0 + lx : -1;
+    }
+    float nxt[NLOAD];
+#pragma unroll
+    for (int j = 0; j < NLOAD; ++j) nxt[j] = ld_off[j] >= 0 ? __ldg(src + ld_off[j]) : 0.f;      // plane 0
+    __syncthreads();
+    for (int zi = 0; zi < D + rd; ++zi) {
+        float *plane = ring[zi % kd];
+        if (zi < D) {
+#pragma unroll
+            for (int j = 0; j < NLOAD; ++j) {
+                const int i = threadIdx.x + j * 256;
+                if (i < ey * ex) s_in[i] = nxt[j];
+            }
+            if (zi + 1 < D) {                          // prefetch the next plane while this one is processed
+                const float *pn = src + (int64_t)(zi + 1) * plane_stride;
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) nxt[j] = ld_off[j] >= 0 ? __ldg(pn + ld_off[j]) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {             // W pass
+                const int i = threadIdx.x + j * 256;
+                if (i < ey * BL_TX) {
+                    const int lx = i % BL_TX, ly = i / BL_TX;
+                    float acc = 0.f;
+                    for (int k = 0; k < kw; ++k) acc += tw[k] * s_in[ly * ex + lx + k];
+                    s_w[i] = acc;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NO; ++j) {             // H pass -> ring
+                const int i = threadIdx.x + j * 256;
+                const int lx = i % BL_TX, ly = i / BL_TX;
+                float acc = 0.f;
+                for (int k = 0; k < kh; ++k) acc += th[k] * s_w[(ly + k) * BL_TX + lx];
+                plane[i] = acc;
+            }
+        }
+        __syncthreads();
+        const int zo = zi - rd;                        // D pass + clamp for plane zo (each thread reads its own ring slots)
+        if (zo >= 0) {
+            float *po = dst + (int64_t)zo * plane_stride;
+#pragma unroll
+            for (int j = 0; j < NO; ++j) {
+                if (st_off[j] < 0) continue;
+                const int i = threadIdx.x + j * 256;
+                float acc = 0.f;
+                for (int k = 0; k < kd; ++k) {
+                    const int z = zo + k - rd;
+                    if (z >= 0 && z < D) acc += td[k] * ring[z % kd][i];
+                }
+                po[st_off[j]] = fminf(fmaxf(acc, 0.f), 1.f);
+            }
+        }
+        // no barrier needed here: the next iteration only overwrites ring[(zi+1) % kd] after two more barriers,
+        // and every thread reads exactly the ring slots it wrote itself
+    }
+}
+
+// Specialisation for the reference's default 3x3x3 kernel (util/arguments.py:25): compile-time tap counts,
+// the D-pass ring lives in registers (each thread only ever reads the planes it produced itself).
+__global__ void __launch_bounds__(256) blur_fused333_kernel(const float *__restrict__ in, float *__restrict__ out, int D, int H, int W,
+                                                            const float *__restrict__ taps_w, const float *__restrict__ taps_h,
+                                                            const float *__restrict__ taps_d) {
+    constexpr int EY = BL_TY + 2, EX = BL_TX + 2;
+    constexpr int NLOAD = (EY * EX + 255) / 256, NW = (EY * BL_TX + 255) / 256, NO = (BL_TY * BL_TX) / 256;
+    __shared__ float s_in[EY * EX];
+    __shared__ float s_w[EY * BL_TX];
+    const float w0 = __ldg(taps_w), w1 = __ldg(taps_w + 1), w2 = __ldg(taps_w + 2);
+    const float h0 = __ldg(taps_h), h1 = __ldg(taps_h + 1), h2 = __ldg(taps_h + 2);
+    const float d0 = __ldg(taps_d), d1 = __ldg(taps_d + 1), d2 = __ldg(taps_d + 2);
+    const int tiles_x = (W + BL_TX - 1) / BL_TX, tiles_y = (H + BL_TY - 1) / BL_TY;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int64_t b = t / tiles_y;
+    const int x0 = tx * BL_TX, y0 = ty * BL_TY;
+    const float *src = in + b * (int64_t)D * H * W;
+    float *dst = out + b * (int64_t)D * H * W;
+    const int64_t plane_stride = (int64_t)H * W;
+    int ld_off[NLOAD];
+#pragma unroll
+    for (int j = 0; j < NLOAD; ++j) {
+        const int i = threadIdx.x + j * 256;
+        ld_off[j] = -1;
+        if (i < EY * EX) {
+            const int lx = i % EX, ly = i / EX;
+            const int x = x0 + lx - 1, y = y0 + ly - 1;
+            if (x >= 0 && x < W && y >= 0 && y < H) ld_off[j] = y * W + x;
+        }
+    }
+    int st_off[NO];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+        const int i = threadIdx.x + j * 256;
+        const int lx = i % BL_TX, ly = i / BL_TX;
+        st_off[j] = (x0 + lx < W && y0 + ly < H) ? (y0 + ly) * W + x0 + lx : -1;
+    }
+    float nxt[NLOAD], prev2[NO], prev1[NO];
+#pragma unroll
+    for (int j = 0; j < NLOAD; ++j) nxt[j] = ld_off[j] >= 0 ? __ldg(src + ld_off[j]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) prev2[j] = prev1[j] = 0.f;
+    for (int zi = 0; zi <= D; ++zi) {
+        float cur[NO];
+#pragma unroll
+        for (int j = 0; j < NO; ++j) cur[j] = 0.f;
+        if (zi < D) {
+#pragma unroll
+            for (int j = 0; j < NLOAD; ++j) {
+                const int i = threadIdx.x + j * 256;
+                if (i < EY * EX) s_in[i] = nxt[j];
+            }
+            if (zi + 1 < D) {
+                const float *pn = src + (int64_t)(zi + 1) * plane_stride;
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) nxt[j] = ld_off[j] >= 0 ? __ldg(pn + ld_off[j]) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const int i = threadIdx.x + j * 256;
+                if (i < EY * BL_TX) {
+                    const int lx = i % BL_TX, ly = i / BL_TX;
+                    const float *r = s_in + ly * EX + lx;
+                    s_w[i] = w0 * r[0] + w1 * r[1] + w2 * r[2];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NO; ++j) {
+                const int i = threadIdx.x + j * 256;
+                const int lx = i % BL_TX, ly = i / BL_TX;
+                const float *r = s_w + ly * BL_TX + lx;
+                cur[j] = h0 * r[0] + h1 * r[BL_TX] + h2 * r[2 * BL_TX];
+            }
+        }
+        if (zi >= 1) {       // output plane zi-1 = d0 * plane(zi-2) + d1 * plane(zi-1) + d2 * plane(zi)
+            float *po = dst + (int64_t)(zi - 1) * plane_stride;
+#pragma unroll
+            for (int j = 0; j < NO; ++j)
+                if (st_off[j] >= 0) po[st_off[j]] = fminf(fmaxf(d0 * prev2[j] + d1 * prev1[j] + d2 * cur[j], 0.f), 1.f);
+        }
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+            prev2[j] = prev1[j];
+            prev1[j] = cur[j];
+        }
+        __syncthreads();     // s_in / s_w are rewritten by the next iteration
+    }
+}
+
 // g3 = gout * [conv_d(t1) <= 1]   (clamp backward with inclusive bounds; values are never < 0)
 __global__ void clamp_mask_kernel(const float *__restrict__ t1, const float *__restrict__ gout, float *__restrict__ g3,
                                   int D, int H, int W, int64_t total, const float *__restrict__ taps, int k) {
@@ -579,6 +785,17 @@ int svr_blur_fwd(const float *in, int B, int D, int H, int W, const float *taps_
     int64_t total = (int64_t)B * D * H * W;
     if (total == 0) return 0;
     cudaStream_t st = as_stream(stream);
+    if (kw <= 2 * BL_MAXR + 1 && kh <= 2 * BL_MAXR + 1 && kd <= 2 * BL_MAXR + 1) {
+        // fused single pass (tmp0/tmp1 unused)
+        const int64_t tiles = (int64_t)B * ceil_div(H, BL_TY) * ceil_div(W, BL_TX);
+        SVR_REQUIRE(tiles < ((int64_t)1 << 31), "blur: too many tiles");
+        if (kw == 3 && kh == 3 && kd == 3)
+            blur_fused333_kernel<<<(unsigned)tiles, 256, 0, st>>>(in, out, D, H, W, taps_w, taps_h, taps_d);
+        else
+            blur_fused_kernel<<<(unsigned)tiles, 256, 0, st>>>(in, out, D, H, W, taps_w, kw, taps_h, kh, taps_d, kd);
+        SVR_LAUNCH_CHECK();
+        return 0;
+    }
     unsigned g = (unsigned)ceil_div<int64_t>(total, 256);
     conv_axis_kernel<<<g, 256, 0, st>>>(in, tmp0, D, H, W, total, 2, taps_w, kw, 0, 0);
     conv_axis_kernel<<<g, 256, 0, st>>>(tmp0, tmp1, D, H, W, total, 1, taps_h, kh, 0, 0);

@@ -115,9 +115,11 @@ class _Blur(torch.autograd.Function):
         tw, th, td = (_dev_f32(t.reshape(-1), "taps") for t in (taps_w, taps_h, taps_d))
         B, D, H, W = g.shape
         out = torch.empty_like(g)
-        tmp = torch.empty((2,) + tuple(g.shape), device=g.device, dtype=torch.float32)
+        fused = max(tw.numel(), th.numel(), td.numel()) <= 7      # single-pass kernel: no scratch grids needed
+        tmp = out if fused else torch.empty((2,) + tuple(g.shape), device=g.device, dtype=torch.float32)
+        t0, t1 = (out, out) if fused else (tmp[0], tmp[1])
         _abi.check(_lib().svr_blur_fwd(g.data_ptr(), B, D, H, W, tw.data_ptr(), tw.numel(), th.data_ptr(), th.numel(),
-                                       td.data_ptr(), td.numel(), out.data_ptr(), tmp[0].data_ptr(), tmp[1].data_ptr(),
+                                       td.data_ptr(), td.numel(), out.data_ptr(), t0.data_ptr(), t1.data_ptr(),
                                        _stream()), "blur_fwd")
         ctx.save_for_backward(g, tw, th, td)
         ctx.shapes = (taps_w.shape, taps_h.shape, taps_d.shape)
