@@ -300,6 +300,25 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _ncu_traffic(profile_name: str, kernel_substr: str):
+    """dram read + write bytes per launch of a kernel from a committed `ncu --set full` summary (profiles/)."""
+    f = ROOT / "profiles" / profile_name
+    if not f.exists():
+        return None
+    unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
+    cur, rd, wr = False, None, None
+    for line in f.read_text().splitlines():
+        if line.startswith("== kernel"):
+            cur = kernel_substr in line
+        elif cur and line.startswith("dram__bytes_read.sum "):
+            v = line.split()
+            rd = float(v[-2]) * unit.get(v[-1], 1.0)
+        elif cur and line.startswith("dram__bytes_write.sum "):
+            v = line.split()
+            wr = float(v[-2]) * unit.get(v[-1], 1.0)
+    return None if rd is None or wr is None else rd + wr
+
+
 def roofline(kms, peaks, net):
     """Roofline of the dominant hot-path kernel (largest share of the step among the IF-Net query kernels).
     Algorithmic bytes / flops per launch are the figures of DESIGN.md section 4."""
@@ -322,7 +341,10 @@ def roofline(kms, peaks, net):
         out.update({"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops_sustained"], "algorithmic_flops": fwd_flops, "algorithmic_bytes": nbytes,
                     "hbm_achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                    "peak_source": peaks["source"] + " (sustained bf16)"})
+                    "peak_source": peaks["source"] + " (sustained bf16)",
+                    "traffic": _ncu_traffic("r1_fused_query_fwd_v2.txt", "fused_query_kernel"),
+                    "traffic_note": "dram read+write per launch, ncu --set full of the same kernel in inference mode "
+                                    "(profiles/r1_fused_query_fwd_v2.txt); the training launch adds the saved features/activations"})
     elif name in ("svr_gather_fwd", "svr_gather_bwd"):
         # gather: volumes + grid in, feature rows out; scatter: d-feature rows in, fp32 gradient volumes written once
         nbytes = (vols_bf16 + x_bytes + M * 12 + M * kp * 2) if name == "svr_gather_fwd" else (M * kp * 2 + 2 * vols_bf16 + M * 12)
