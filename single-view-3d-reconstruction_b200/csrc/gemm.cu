@@ -339,30 +339,66 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, int spli
 // ------------------------------------------------------------------------------------------------
 // small helpers of the decoder backward
 // ------------------------------------------------------------------------------------------------
-// dz2 = dlogit (x) wout masked by h2 > 0;  per-block partials of gwout / gbout
+// dz2 = dlogit (x) wout masked by h2 > 0;  per-block partials of gwout / gbout.
+// thread = (row lane, 8-column group): 16-byte loads/stores, 512 B per row and warp.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float *__restrict__ dlogit, const int *__restrict__ perm,
-                                                       const __nv_bfloat16 *__restrict__ h2,
-                                                       const float *__restrict__ wout, int M, int Hd,
+                                                       const __nv_bfloat16 *__restrict__ h2, const float *__restrict__ wout, int M, int Hd,
                                                        __nv_bfloat16 *__restrict__ dz2, float *__restrict__ part_w,
                                                        float *__restrict__ part_b, int rows_per_block) {
-    // thread t owns column t (Hd <= 256); the block walks its rows
-    const int col = threadIdx.x;
+    __shared__ float red_w[8][256];
+    __shared__ float red_b[8];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;        // 32 column groups (256 columns) x 8 row lanes
+    const int c0 = cg * 8;
+    const bool col_ok = c0 < Hd;
     const int r0 = blockIdx.x * rows_per_block;
     int r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
-    float gw = 0.f, gb = 0.f;
-    const float w = col < Hd ? wout[col] : 0.f;
-    for (int r = r0; r < r1; ++r) {
-        float dl = dlogit[perm ? perm[r] : r];
-        if (col < Hd) {
-            float h = __bfloat162float(h2[(int64_t)r * Hd + col]);
-            gw += dl * h;
-            dz2[(int64_t)r * Hd + col] = __float2bfloat16(h > 0.f ? dl * w : 0.f);
-        }
-        gb += dl;
+    float w[8], gw[8], gb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        w[j] = (col_ok && c0 + j < Hd) ? wout[c0 + j] : 0.f;
+        gw[j] = 0.f;
     }
-    if (col < Hd) part_w[(int64_t)blockIdx.x * Hd + col] = gw;
-    if (col == 0) part_b[blockIdx.x] = gb;
+    for (int r = r0 + rl; r < r1; r += 8) {
+        const float dl = dlogit[perm ? perm[r] : r];
+        if (cg == 0) gb += dl;
+        if (col_ok) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(h2 + (int64_t)r * Hd + c0);
+            const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
+            float h[8], o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[2 * j] = __uint_as_float(ww[j] << 16);
+                h[2 * j + 1] = __uint_as_float(ww[j] & 0xffff0000u);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                gw[j] = fmaf(dl, h[j], gw[j]);
+                o[j] = h[j] > 0.f ? dl * w[j] : 0.f;
+            }
+            __nv_bfloat162 pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+            *reinterpret_cast<uint4 *>(dz2 + (int64_t)r * Hd + c0) = *reinterpret_cast<uint4 *>(pk);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red_w[rl][c0 + j] = gw[j];
+    if (cg == 0) red_b[rl] = gb;
+    __syncthreads();
+    const int col = threadIdx.x;
+    if (col < Hd) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += red_w[q][col];
+        part_w[(int64_t)blockIdx.x * Hd + col] = v;
+    }
+    if (col == 0) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += red_b[q];
+        part_b[blockIdx.x] = v;
+    }
 }
 
 __global__ void head_bwd_reduce_kernel(const float *__restrict__ part_w, const float *__restrict__ part_b, int nblocks,
@@ -380,16 +416,39 @@ __global__ void head_bwd_reduce_kernel(const float *__restrict__ part_w, const f
     }
 }
 
+// column sums of a bf16 (M, N) matrix: thread = (row lane, 8-column group), 16-byte loads
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16 *__restrict__ a, int M, int N, int64_t lda,
                                                              int rows_per_block, float *__restrict__ part) {
+    __shared__ float red[8][256];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + cg * 8;
     const int r0 = blockIdx.y * rows_per_block;
     int r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= N) return;
-    float v = 0.f;
-    for (int r = r0; r < r1; ++r) v += __bfloat162float(a[(int64_t)r * lda + col]);
-    part[(int64_t)blockIdx.y * N + col] = v;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (c0 < N) {
+        for (int r = r0 + rl; r < r1; r += 8) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(a + (int64_t)r * lda + c0);
+            const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[2 * j] += __uint_as_float(ww[j] << 16);
+                acc[2 * j + 1] += __uint_as_float(ww[j] & 0xffff0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+    __syncthreads();
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += red[q][threadIdx.x];
+        part[(int64_t)blockIdx.y * N + col] = v;
+    }
 }
 
 __global__ void colsum_reduce_kernel(const float *__restrict__ part, int nblocks, int N, float *__restrict__ out,
@@ -507,7 +566,7 @@ int svr_gemm_tn(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, 
 int svr_decoder_head_bwd(const float *dlogit, const int *perm, const uint16_t *h2, const float *wout, int M, int Hd,
                          uint16_t *dz2, float *gwout, float *gbout, void *stream) {
     SVR_REQUIRE(dlogit && h2 && wout && dz2 && gwout && gbout, "decoder_head_bwd: null pointer");
-    SVR_REQUIRE(Hd > 0 && Hd <= 256, "decoder_head_bwd: hidden size must be <= 256");
+    SVR_REQUIRE(Hd > 0 && Hd <= 256 && Hd % 8 == 0, "decoder_head_bwd: hidden size must be a multiple of 8 and <= 256");
     if (M == 0) return 0;
     cudaStream_t st = as_stream(stream);
     const int rows_per_block = ceil_div(M, 4 * sm_count()) > 16 ? ceil_div(M, 4 * sm_count()) : 16;
@@ -523,7 +582,7 @@ int svr_decoder_head_bwd(const float *dlogit, const int *perm, const uint16_t *h
 }
 
 int svr_colsum_bf16(const uint16_t *a, int M, int N, int64_t lda, float *out, int accumulate, void *stream) {
-    SVR_REQUIRE(a && out && N > 0, "colsum: bad arguments");
+    SVR_REQUIRE(a && out && N > 0 && N % 8 == 0 && lda % 8 == 0, "colsum: N and lda must be positive multiples of 8");
     cudaStream_t st = as_stream(stream);
     if (M == 0) {
         if (!accumulate) SVR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
