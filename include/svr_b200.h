@@ -206,6 +206,18 @@ int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, cons
                         const svr_decoder_weights *w_host, float *logits, uint16_t *save_h,
                         uint16_t *save_feat, int apply_sigmoid, void *stream);
 
+/* Fused decoder backward-data chain (Conv1d backward of ifnet.py:55-58, hidden size 256):
+ *   dz1 = (dz2 . W2) * [h1 > 0],  dz0 = (dz1 . W1) * [h0 > 0],  dfeat = dz0 . W0'   (all bf16, row-major)
+ * in one persistent tcgen05 kernel.  Weights are pre-swizzled chunk images (svr_pack_decoder_image) of
+ * W2^T (256,256), W1^T (256,256) and W0'^T (KP,256).                                              */
+int svr_decoder_bwd_fused(const uint16_t *dz2, const uint16_t *h1, const uint16_t *h0, const void *w2t_img,
+                          const void *w1t_img, const void *w0pt_img, int64_t M, int kp, uint16_t *dz1, uint16_t *dz0,
+                          uint16_t *dfeat, void *stream);
+
+/* Debug: device buffer of 3*1024*2 int64 (tag, SM clock) records that block 0 of the following
+ * svr_decoder_bwd_fused launches fills (row worker / MMA / loader roles); NULL switches tracing off.  */
+int svr_debug_fb_trace(void *buf);
+
 /* Dense evaluation (evaluate_network_on_grid, ifnet.py:215-229; make_3d_grid :202-212): evaluates
  * sigmoid(decoder(sample(x, lattice))) on the (sx,sy,sz) inclusive lattice over [-0.5,0.5]^3 for
  * z-slab [x_begin, x_end) of the FIRST lattice axis, generating the points on the fly; out is the

@@ -1,5 +1,6 @@
 // Error plumbing and device queries of the svr_b200 C-ABI library.
 #include "common.cuh"
+#include <cuda.h>
 #include <cstring>
 
 namespace svr {
@@ -24,6 +25,42 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+int make_tmap_bf16_sw128(TensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) == alignof(CUtensorMap), "TensorMap layout");
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;   // resolved through the runtime: no link-time libcuda dependency
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+            return -1;
+        }
+        encode = (EncodeFn)fn;
+    }
+    if (((uintptr_t)base & 15) || (ld * 2) % 16 || cols % 64 || box_rows < 1 || box_rows > 256) {
+        set_error("tensor map: base must be 16-byte aligned, ld*2 a multiple of 16, cols a multiple of 64 (ld=%lld cols=%lld)", (long long)ld,
+                  (long long)cols);
+        return -1;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode((CUtensorMap *)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows, (long long)cols,
+                  (long long)ld);
+        return -1;
+    }
+    return 0;
 }
 
 }  // namespace svr

@@ -46,6 +46,14 @@ static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 int sm_count();   // cached per device
 
+// 128-byte opaque TMA descriptor (same layout and alignment as the driver's CUtensorMap)
+struct alignas(64) TensorMap {
+    uint64_t opaque[16];
+};
+// row-major bf16 matrix (rows x cols, leading dimension ld elements) tiled in boxes of box_rows x 64 columns
+// with the 128-byte swizzle the UMMA K-major operand layout uses.  0 on success.
+int make_tmap_bf16_sw128(TensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
 // small POD passed by value to kernels
 struct Dims3 {
     int d[3];

@@ -121,9 +121,6 @@ __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw) {
     return s;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 template <int FQ_GATHER_WARPS>
 __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_kernel(const FqParams p, int64_t n_tiles) {

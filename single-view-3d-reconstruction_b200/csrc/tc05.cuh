@@ -72,6 +72,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA 2-D tiled copies through a CUtensorMap (UTMALDG / UTMASTG); coordinates are {inner, outer} elements
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, uint32_t src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until at most N of this thread's bulk groups are incomplete (writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM management
 // ---------------------------------------------------------------------------------------------
 // one full warp; writes the TMEM base address to *dst_smem; ncols power of two in [32,512]

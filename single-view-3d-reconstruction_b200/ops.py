@@ -278,13 +278,28 @@ class PackedDecoder:
             _abi.check(_lib().svr_pack_matrix(w1f.data_ptr(), h1, h0, t["w1"].data_ptr(), t["w1T"].data_ptr(), st), "pack_matrix")
             _abi.check(_lib().svr_pack_matrix(w2f.data_ptr(), h2, h1, t["w2"].data_ptr(), t["w2T"].data_ptr(), st), "pack_matrix")
             if h0 == h1 == h2 == 256:    # pre-swizzled UMMA chunk images for the fused forward kernel
-                for name in ("w0p", "w1", "w2"):
-                    img = torch.empty((t[name].numel() * 2,), device=dev, dtype=torch.uint8)
-                    _abi.check(_lib().svr_pack_decoder_image(t[name].data_ptr(), t[name].shape[0], t[name].shape[1], img.data_ptr(), st),
-                               "pack_decoder_image")
-                    t[name + "_img"] = img
+                for name in ("w0p", "w1", "w2", "w0pT", "w1T", "w2T"):
+                    t[name + "_img"] = swizzled_image(t[name])
             self.t, self.key = t, key
         return self.t
+
+
+def swizzled_image(w):
+    """(R, K) bf16 row-major matrix -> the K-chunked 128-byte-swizzled operand image the fused kernels stream."""
+    img = torch.empty((w.numel() * 2,), device=w.device, dtype=torch.uint8)
+    _abi.check(_lib().svr_pack_decoder_image(w.data_ptr(), w.shape[0], w.shape[1], img.data_ptr(), _stream()), "pack_decoder_image")
+    return img
+
+
+def decoder_bwd_fused(dz2, h1, h0, w2T_img, w1T_img, w0pT_img, kp):
+    """dz1 = (dz2 W2)*[h1>0], dz0 = (dz1 W1)*[h0>0], dfeat = dz0 W0' (bf16) in one persistent kernel (hidden size 256)."""
+    M = dz2.shape[0]
+    dz1, dz0 = torch.empty_like(dz2), torch.empty_like(dz2)
+    dfeat = torch.empty((M, kp), device=dz2.device, dtype=_BF16)
+    _abi.check(_lib().svr_decoder_bwd_fused(dz2.data_ptr(), h1.data_ptr(), h0.data_ptr(), w2T_img.data_ptr(), w1T_img.data_ptr(),
+                                            w0pT_img.data_ptr(), M, kp, dz1.data_ptr(), dz0.data_ptr(), dfeat.data_ptr(), _stream()),
+               "decoder_bwd_fused")
+    return dz1, dz0, dfeat
 
 
 def _gemm_nt(A, B, bias, M, N, K, flags, c_bf16=None, c_f32=None, ldc=0, mask=None, dot_w=None, dot_b=None, out_dot=None):
@@ -301,6 +316,7 @@ def _gemm_tn(A, B, M, N, P, out, accumulate=False):
 
 RELU, ST_BF16, ST_F32, MASK, DOT = 1, 2, 4, 8, 16
 USE_FUSED = True     # fused gather+decoder forward kernel when the decoder is 256/256/256
+USE_FUSED_BWD = True  # fused decoder backward-data chain (dz1, dz0, dfeat) when the decoder is 256/256/256
 SORT_MIN_POINTS = 2048   # spatially sort the query points of a scene when it has at least this many
 
 
@@ -447,13 +463,19 @@ class _Query(torch.autograd.Function):
         gw2 = torch.empty((h2n, h1n), device=dev, dtype=torch.float32)
         _gemm_tn(dz2, h1, h2n, h1n, M, gw2)
         gb2 = colsum(dz2, h2n)
-        dz1 = torch.empty((M, h1n), device=dev, dtype=_BF16)
-        _gemm_nt(dz2, W["w2T"], None, M, h1n, h2n, ST_BF16 | MASK, c_bf16=dz1, ldc=h1n, mask=h1)
+        need_dfeat = any(m[2] for m in ctx.vol_meta) or ctx.x_needs or ctx.p_needs
+        dfeat = None
+        fused_bwd = USE_FUSED_BWD and "w0pT_img" in W
+        if fused_bwd:   # dz1, dz0 and dfeat in one persistent kernel
+            dz1, dz0, dfeat = decoder_bwd_fused(dz2, h1, h0, W["w2T_img"], W["w1T_img"], W["w0pT_img"], pyr.kp)
+        else:
+            dz1 = torch.empty((M, h1n), device=dev, dtype=_BF16)
+            dz0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
+            _gemm_nt(dz2, W["w2T"], None, M, h1n, h2n, ST_BF16 | MASK, c_bf16=dz1, ldc=h1n, mask=h1)
+            _gemm_nt(dz1, W["w1T"], None, M, h0n, h1n, ST_BF16 | MASK, c_bf16=dz0, ldc=h0n, mask=h0)
         gw1 = torch.empty((h1n, h0n), device=dev, dtype=torch.float32)
         _gemm_tn(dz1, h0, h1n, h0n, M, gw1)
         gb1 = colsum(dz1, h1n)
-        dz0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
-        _gemm_nt(dz1, W["w1T"], None, M, h0n, h1n, ST_BF16 | MASK, c_bf16=dz0, ldc=h0n, mask=h0)
         gw0p = torch.empty((h0n, pyr.kp), device=dev, dtype=torch.float32)
         _gemm_tn(dz0, feat, h0n, pyr.kp, M, gw0p)
         gw0 = torch.empty((h0n, pyr.k), device=dev, dtype=torch.float32)
@@ -464,8 +486,9 @@ class _Query(torch.autograd.Function):
         gvols_out: List[Optional[torch.Tensor]] = [None] * len(packed)
         gx = gp = None
         if any_vol or ctx.x_needs or ctx.p_needs:
-            dfeat = torch.empty((M, pyr.kp), device=dev, dtype=_BF16)
-            _gemm_nt(dz0, W["w0pT"], None, M, pyr.kp, h0n, ST_BF16, c_bf16=dfeat, ldc=pyr.kp)
+            if dfeat is None:
+                dfeat = torch.empty((M, pyr.kp), device=dev, dtype=_BF16)
+                _gemm_nt(dz0, W["w0pT"], None, M, pyr.kp, h0n, ST_BF16, c_bf16=dfeat, ldc=pyr.kp)
             gbufs = []
             for i, (shape, _, needs) in enumerate(ctx.vol_meta):
                 Bv, Cv, Dv, Hv, Wv = shape
