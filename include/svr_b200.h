@@ -206,6 +206,24 @@ int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, cons
                         const svr_decoder_weights *w_host, float *logits, uint16_t *save_h,
                         uint16_t *save_feat, int apply_sigmoid, void *stream);
 
+/* First stage of the 128-net fused: y = BatchNorm3d(relu(Conv3d(1 -> 16, 3, padding 1)(x))), channels-last y
+ * (model/ifnet.py:126,137,164 `net = self.actvn(self.conv_in(x)); net = self.conv_in_bn(net)`).  The pre-BN
+ * activation is never stored: every pass recomputes it from the one-channel input.
+ *   stats : training-mode batch mean / 1/sqrt(var+eps) (biased variance) into mean[16], invstd[16]; running_mean /
+ *           running_var (nullable) get torch's momentum update (unbiased variance).
+ *   apply : y (B,D,H,W,16) from given mean / invstd (batch statistics, or running statistics in eval mode).
+ *   bwd   : gw (16,27), gb (16), ggamma (16), gbeta (16) from gy (B,D,H,W,16), training-mode BN backward.
+ * x (B,D,H,W) fp32, w (16,27), bias / gamma / beta nullable.  Workspace: svr_conv1_bn_workspace_bytes().       */
+size_t svr_conv1_bn_workspace_bytes(void);
+int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, int B, int D, int H, int W, int Co, float eps,
+                            float momentum, float *running_mean, float *running_var, float *mean, float *invstd, void *workspace,
+                            size_t workspace_bytes, void *stream);
+int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, const float *mean, const float *invstd,
+                            const float *gamma, const float *beta, int B, int D, int H, int W, int Co, float *y, void *stream);
+int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, const float *mean, const float *invstd,
+                          const float *gamma, const float *gy, int B, int D, int H, int W, int Co, float *gw, float *gb,
+                          float *ggamma, float *gbeta, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Fused decoder backward-data chain (Conv1d backward of ifnet.py:55-58, hidden size 256):
  *   dz1 = (dz2 . W2) * [h1 > 0],  dz0 = (dz1 . W1) * [h0 > 0],  dfeat = dz0 . W0'   (all bf16, row-major)
  * in one persistent tcgen05 kernel.  Weights are pre-swizzled chunk images (svr_pack_decoder_image) of

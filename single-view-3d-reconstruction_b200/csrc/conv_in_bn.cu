@@ -1,0 +1,532 @@
+// First encoder stage of the 128-net fused end to end:  y = BatchNorm3d(relu(Conv3d(1 -> 16, 3x3x3, pad 1)(x)))
+// (model/ifnet.py:126,137,164 of the reference: `net = self.actvn(self.conv_in(x)); net = self.conv_in_bn(net)`),
+// training-mode batch statistics included, channels-last output.
+//
+// The pre-BN activation a = relu(conv(x)) is a 0.54 GB tensor at batch 4 x 128^3, yet it is a 27-tap stencil
+// of a ONE-channel input (33 MB): recomputing it is cheaper than storing and re-reading it.  So instead of
+//   conv+ReLU (write a) -> BN statistics (read a) -> BN apply (read a, write y)            forward
+//   BN backward (read a, gy twice, write da) -> ReLU mask + wgrad (read a, da)              backward
+// the stage becomes four streaming passes that only ever touch x, y and gy:
+//   stats   : a recomputed, per-channel sum / sum of squares            (reads x)
+//   apply   : a recomputed, y = a * s + t                               (reads x, writes y)
+//   bwd 1   : a recomputed, sum gy and sum gy * xhat                    (reads x, gy)
+//   bwd 2   : a recomputed, da -> ReLU mask -> weight/bias gradient     (reads x, gy)
+// `a` is recomputed by the same inlined routine everywhere, so the ReLU mask of the backward pass is
+// bit-identical to the forward activation.
+//
+// Work unit: a warp owns a 64-voxel segment of an x-row; the 3x3 neighbouring rows (with halo) are staged in
+// a warp-private shared tile, lane v computes the 16 channels of voxels v and v+32 (f32x2 FMAs, one broadcast
+// weight load serves both voxels).  The weight gradient dW[ch][tap] = sum_vox dz[vox][ch] * x[vox + tap] is a
+// (16 x 64) . (64 x 32) product per segment: the masked gradients are parked in shared memory and multiplied
+// on the tensor cores with mma.sync m16n8k8 TF32, dz split into a TF32 head and tail (two MMAs) so that only
+// x is rounded to TF32 (exact for occupancy grids; cuDNN's default wgrad rounds both operands).
+#include "common.cuh"
+
+namespace svr {
+
+constexpr int CB_CO = 16;
+constexpr int CB_WARPS = 8;
+constexpr int CB_SEG = 64;                // voxels per segment
+constexpr int CB_RS = 72;                 // tile row stride in floats (66 used); 72 = 8 mod 32 keeps the taps of an
+                                          // MMA operand load on distinct banks
+constexpr int CB_TILE = 11 * CB_RS;       // 9 stencil rows + a row of ones (bias "tap") + a row of zeros
+constexpr int CB_DS = 24;                 // stride of a parked gradient row (16 used): 4 voxel rows x 8 channels conflict-free
+
+struct CbGeom {
+    int B, D, H, W, segs_per_row, n_segs;
+    int64_t n_vox;
+};
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2 &acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ uint32_t to_tf32(float f) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct CbShared {
+    ulonglong2 wt[27][CB_CO / 4];         // [tap][channel quad] as two f32x2 pairs
+    float4 bs[CB_CO / 4];
+    float ch[4][CB_CO];                   // per-channel constants of the pass
+    float tile[CB_WARPS][CB_TILE];
+};
+
+__device__ __forceinline__ void cb_load_weights(CbShared &s, const float *__restrict__ w, const float *__restrict__ bias) {
+    for (int i = threadIdx.x; i < 27 * CB_CO; i += blockDim.x) {
+        const int co = i / 27, tap = i - co * 27;
+        reinterpret_cast<float *>(&s.wt[tap][0])[co] = w[i];
+    }
+    if (threadIdx.x < CB_CO) reinterpret_cast<float *>(s.bs)[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = lane; e < CB_RS; e += 32) {
+        s.tile[warp][9 * CB_RS + e] = 1.f;
+        s.tile[warp][10 * CB_RS + e] = 0.f;
+    }
+}
+
+// segment -> voxel index of its first voxel and x0; stages the 3x3 rows x0-1 .. x0+64 of x in the warp's tile
+// (tile[r][e] = x at x0 - 1 + e)
+__device__ __forceinline__ int64_t cb_stage(const CbGeom &g, const float *__restrict__ x, int seg, int lane, float *tile, int &x0) {
+    const int row = seg / g.segs_per_row;
+    x0 = (seg - row * g.segs_per_row) * CB_SEG;
+    const int yy = row % g.H, r2 = row / g.H;
+    const int zz = r2 % g.D, b = r2 / g.D;
+    const int64_t base = (((int64_t)b * g.D + zz) * g.H + yy) * g.W;
+    __syncwarp();                                     // the previous segment's readers are done
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int z = zz + r / 3 - 1, yq = yy + r % 3 - 1;
+        const bool row_ok = z >= 0 && z < g.D && yq >= 0 && yq < g.H;
+        const float *src = x + base + ((int64_t)(r / 3 - 1) * g.H + (r % 3 - 1)) * g.W;
+        const int xa = x0 - 1 + lane, xb = xa + 32;
+        tile[r * CB_RS + lane] = (row_ok && xa >= 0 && xa < g.W) ? __ldg(src + xa) : 0.f;
+        tile[r * CB_RS + 32 + lane] = (row_ok && xb < g.W) ? __ldg(src + xb) : 0.f;
+        if (lane < 2) {
+            const int xc = x0 + 63 + lane;
+            tile[r * CB_RS + 64 + lane] = (row_ok && xc < g.W) ? __ldg(src + xc) : 0.f;
+        }
+    }
+    __syncwarp();
+    return base + x0;
+}
+
+// a[j][c] = relu(bias[c] + sum_tap w[c][tap] * x[voxel_j + tap]) for the lane's voxels lane and lane+32 (fixed
+// accumulation order: the same bits in every pass)
+__device__ __forceinline__ void cb_conv_relu(const CbShared &s, const float *tile, int lane, float (&a)[2][CB_CO]) {
+    f32x2 acc[2][CB_CO / 2];
+#pragma unroll
+    for (int c = 0; c < CB_CO / 4; ++c) {
+        acc[0][2 * c] = acc[1][2 * c] = pack2(s.bs[c].x, s.bs[c].y);
+        acc[0][2 * c + 1] = acc[1][2 * c + 1] = pack2(s.bs[c].z, s.bs[c].w);
+    }
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+        const float v0 = tile[(tap / 3) * CB_RS + lane + tap % 3], v1 = tile[(tap / 3) * CB_RS + 32 + lane + tap % 3];
+        const f32x2 vv0 = pack2(v0, v0), vv1 = pack2(v1, v1);
+#pragma unroll
+        for (int c = 0; c < CB_CO / 4; ++c) {
+            const ulonglong2 w = s.wt[tap][c];
+            fma2(acc[0][2 * c], vv0, w.x);
+            fma2(acc[0][2 * c + 1], vv0, w.y);
+            fma2(acc[1][2 * c], vv1, w.x);
+            fma2(acc[1][2 * c + 1], vv1, w.y);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < CB_CO / 2; ++c) {
+            float lo, hi;
+            unpack2(acc[j][c], lo, hi);
+            a[j][2 * c] = fmaxf(lo, 0.f);
+            a[j][2 * c + 1] = fmaxf(hi, 0.f);
+        }
+}
+
+// sum the 2*CB_CO per-lane accumulators over the block, one row of `partial` per block
+__device__ __forceinline__ void cb_block_reduce32(float (&s1)[CB_CO], float (&s2)[CB_CO], float *red /* [CB_WARPS][32] */, float *__restrict__ partial) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < CB_CO; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+            s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+        }
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < CB_CO; ++c) {
+            red[warp * 32 + c] = s1[c];
+            red[warp * 32 + CB_CO + c] = s2[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = 0.f;
+        for (int w = 0; w < CB_WARPS; ++w) v += red[w * 32 + threadIdx.x];
+        partial[(int64_t)blockIdx.x * 32 + threadIdx.x] = v;
+    }
+}
+
+// ---- forward pass 1: batch statistics of a -------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_WARPS * 32) cb_stats_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                 const float *__restrict__ bias, const CbGeom g, float *__restrict__ partial) {
+    __shared__ CbShared s;
+    cb_load_weights(s, w, bias);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tile = s.tile[warp];
+    float s1[CB_CO], s2[CB_CO];
+#pragma unroll
+    for (int c = 0; c < CB_CO; ++c) s1[c] = s2[c] = 0.f;
+    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
+        int x0;
+        cb_stage(g, x, seg, lane, tile, x0);
+        float a[2][CB_CO];
+        cb_conv_relu(s, tile, lane, a);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (x0 + lane + 32 * j < g.W) {
+#pragma unroll
+                for (int c = 0; c < CB_CO; ++c) {
+                    s1[c] += a[j][c];
+                    s2[c] = fmaf(a[j][c], a[j][c], s2[c]);
+                }
+            }
+    }
+    cb_block_reduce32(s1, s2, &s.tile[0][0], partial);   // the tiles are free after the loop (barrier inside)
+}
+
+// mean / inverse standard deviation from the block partials (double), running statistics updated like
+// torch.nn.BatchNorm3d (momentum update with the unbiased variance)
+__global__ void cb_stats_finalize_kernel(const float *__restrict__ partial, int nblocks, double n, float eps, float momentum,
+                                         float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
+                                         float *__restrict__ invstd) {
+    __shared__ double acc[32][32];
+    const int col = threadIdx.x & 31, part = threadIdx.x >> 5;   // 1024 threads
+    double v = 0.0;
+    for (int b = part; b < nblocks; b += 32) v += (double)partial[(int64_t)b * 32 + col];
+    acc[part][col] = v;
+    __syncthreads();
+    if (threadIdx.x < CB_CO) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int p = 0; p < 32; ++p) {
+            s1 += acc[p][threadIdx.x];
+            s2 += acc[p][CB_CO + threadIdx.x];
+        }
+        const double m = s1 / n;
+        double var = s2 / n - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[threadIdx.x] = (float)m;
+        invstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) running_mean[threadIdx.x] = (1.f - momentum) * running_mean[threadIdx.x] + momentum * (float)m;
+        if (running_var) {
+            const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+            running_var[threadIdx.x] = (1.f - momentum) * running_var[threadIdx.x] + momentum * (float)unbiased;
+        }
+    }
+}
+
+// ---- forward pass 2: y = (a - mean) * invstd * gamma + beta ------------------------------------------------------
+__global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                 const float *__restrict__ bias, const float *__restrict__ mean,
+                                                                 const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                                                 const float *__restrict__ beta, const CbGeom g, float *__restrict__ y) {
+    __shared__ CbShared s;
+    cb_load_weights(s, w, bias);
+    if (threadIdx.x < CB_CO) {
+        const float sc = (gamma ? gamma[threadIdx.x] : 1.f) * invstd[threadIdx.x];
+        s.ch[0][threadIdx.x] = sc;
+        s.ch[1][threadIdx.x] = (beta ? beta[threadIdx.x] : 0.f) - mean[threadIdx.x] * sc;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tile = s.tile[warp];
+    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
+        int x0;
+        const int64_t p0 = cb_stage(g, x, seg, lane, tile, x0);
+        float a[2][CB_CO];
+        cb_conv_relu(s, tile, lane, a);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (x0 + lane + 32 * j < g.W) {
+                float4 *dst = reinterpret_cast<float4 *>(y + (p0 + lane + 32 * j) * CB_CO);
+#pragma unroll
+                for (int c = 0; c < CB_CO / 4; ++c)
+                    dst[c] = make_float4(fmaf(a[j][4 * c], s.ch[0][4 * c], s.ch[1][4 * c]), fmaf(a[j][4 * c + 1], s.ch[0][4 * c + 1], s.ch[1][4 * c + 1]),
+                                         fmaf(a[j][4 * c + 2], s.ch[0][4 * c + 2], s.ch[1][4 * c + 2]),
+                                         fmaf(a[j][4 * c + 3], s.ch[0][4 * c + 3], s.ch[1][4 * c + 3]));
+            }
+    }
+}
+
+// ---- backward pass 1: sum gy, sum gy * xhat ---------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_WARPS * 32) cb_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                      const float *__restrict__ bias, const float *__restrict__ mean,
+                                                                      const float *__restrict__ invstd, const float *__restrict__ gy,
+                                                                      const CbGeom g, float *__restrict__ partial) {
+    __shared__ CbShared s;
+    cb_load_weights(s, w, bias);
+    if (threadIdx.x < CB_CO) {
+        s.ch[0][threadIdx.x] = mean[threadIdx.x];
+        s.ch[1][threadIdx.x] = invstd[threadIdx.x];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tile = s.tile[warp];
+    float s1[CB_CO], s2[CB_CO];
+#pragma unroll
+    for (int c = 0; c < CB_CO; ++c) s1[c] = s2[c] = 0.f;
+    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
+        int x0;
+        const int64_t p0 = cb_stage(g, x, seg, lane, tile, x0);
+        float4 gq[2][CB_CO / 4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool ok = x0 + lane + 32 * j < g.W;
+            const float4 *src = reinterpret_cast<const float4 *>(gy + (p0 + lane + 32 * j) * CB_CO);
+#pragma unroll
+            for (int c = 0; c < CB_CO / 4; ++c) gq[j][c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float a[2][CB_CO];
+        cb_conv_relu(s, tile, lane, a);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < CB_CO / 4; ++c) {
+                const float gv[4] = {gq[j][c].x, gq[j][c].y, gq[j][c].z, gq[j][c].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ch = 4 * c + e;
+                    const float xh = (a[j][ch] - s.ch[0][ch]) * s.ch[1][ch];
+                    s1[ch] += gv[e];
+                    s2[ch] = fmaf(gv[e], xh, s2[ch]);
+                }
+            }
+    }
+    cb_block_reduce32(s1, s2, &s.tile[0][0], partial);
+}
+
+// ggamma = sum gy * xhat, gbeta = sum gy (double reduce of the block partials)
+__global__ void cb_bwd_finalize_kernel(const float *__restrict__ partial, int nblocks, float *__restrict__ gbeta, float *__restrict__ ggamma) {
+    __shared__ double acc[32][32];
+    const int col = threadIdx.x & 31, part = threadIdx.x >> 5;   // 1024 threads
+    double v = 0.0;
+    for (int b = part; b < nblocks; b += 32) v += (double)partial[(int64_t)b * 32 + col];
+    acc[part][col] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (int p = 0; p < 32; ++p) t += acc[p][threadIdx.x];
+        if (threadIdx.x < CB_CO)
+            gbeta[threadIdx.x] = (float)t;
+        else
+            ggamma[threadIdx.x - CB_CO] = (float)t;
+    }
+}
+
+// ---- backward pass 2: da = gamma * invstd * (gy - mean(gy) - xhat * mean(gy * xhat)), ReLU mask, weight gradient -----
+__global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                     const float *__restrict__ bias, const float *__restrict__ mean,
+                                                                     const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                                                     const float *__restrict__ gbeta, const float *__restrict__ ggamma,
+                                                                     const float *__restrict__ gy, const CbGeom g, float inv_n,
+                                                                     float *__restrict__ partial /* [grid][28][16] */) {
+    extern __shared__ __align__(16) uint8_t cb_dyn[];
+    CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
+    float *park = reinterpret_cast<float *>(cb_dyn + sizeof(CbShared));   // [CB_WARPS][CB_SEG][CB_DS]
+    __shared__ float k1[CB_CO];
+    cb_load_weights(s, w, bias);
+    if (threadIdx.x < CB_CO) {
+        s.ch[0][threadIdx.x] = mean[threadIdx.x];
+        s.ch[1][threadIdx.x] = invstd[threadIdx.x];
+        s.ch[2][threadIdx.x] = (gamma ? gamma[threadIdx.x] : 1.f) * invstd[threadIdx.x];
+        s.ch[3][threadIdx.x] = ggamma[threadIdx.x] * inv_n;
+        k1[threadIdx.x] = gbeta[threadIdx.x] * inv_n;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tile = s.tile[warp];
+    float *dz = park + warp * (CB_SEG * CB_DS);
+    // MMA roles (m16n8k8: M = channel, N = tap, K = voxel): gq = lane / 4, t = lane % 4.
+    //   A (dz^T)  a0 (ch gq, vox t)  a1 (ch gq+8, vox t)  a2 (ch gq, vox t+4)  a3 (ch gq+8, vox t+4)
+    //   B (xcol)  b0 (vox t, tap gq + 8 nb)  b1 (vox t+4, tap gq + 8 nb);   tap 27 = row of ones (bias), > 27 = zeros
+    //   C         c0 (ch gq, tap 8nb+2t)  c1 (ch gq, tap 8nb+2t+1)  c2 (ch gq+8, tap 8nb+2t)  c3 (ch gq+8, tap 8nb+2t+1)
+    const int gq = lane >> 2, t = lane & 3;
+    int toff[4];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        const int tap = gq + 8 * nb;
+        toff[nb] = (tap < 27 ? (tap / 3) * CB_RS + tap % 3 : (tap == 27 ? 9 * CB_RS : 10 * CB_RS)) + t;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
+    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
+        int x0;
+        const int64_t p0 = cb_stage(g, x, seg, lane, tile, x0);   // leading __syncwarp: last segment's parked rows are consumed
+        float4 gv4[2][CB_CO / 4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool ok = x0 + lane + 32 * j < g.W;
+            const float4 *src = reinterpret_cast<const float4 *>(gy + (p0 + lane + 32 * j) * CB_CO);
+#pragma unroll
+            for (int c = 0; c < CB_CO / 4; ++c) gv4[j][c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float a[2][CB_CO];
+        cb_conv_relu(s, tile, lane, a);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool ok = x0 + lane + 32 * j < g.W;
+#pragma unroll
+            for (int c = 0; c < CB_CO / 4; ++c) {
+                const float gv[4] = {gv4[j][c].x, gv4[j][c].y, gv4[j][c].z, gv4[j][c].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ch = 4 * c + e;
+                    const float xh = (a[j][ch] - s.ch[0][ch]) * s.ch[1][ch];
+                    const float da = s.ch[2][ch] * (gv[e] - k1[ch] - xh * s.ch[3][ch]);
+                    o[e] = (ok && a[j][ch] > 0.f) ? da : 0.f;
+                }
+                *reinterpret_cast<float4 *>(dz + (lane + 32 * j) * CB_DS + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int kb = 0; kb < CB_SEG / 8; ++kb) {
+            const float *dr = dz + (8 * kb + t) * CB_DS + gq;
+            const float af[4] = {dr[0], dr[8], dr[4 * CB_DS], dr[4 * CB_DS + 8]};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                hi[e] = to_tf32(af[e]);
+                lo[e] = to_tf32(af[e] - __uint_as_float(hi[e]));
+            }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const uint32_t b0 = to_tf32(tile[toff[nb] + 8 * kb]), b1 = to_tf32(tile[toff[nb] + 8 * kb + 4]);
+                mma_tf32(acc[nb], hi, b0, b1);
+                mma_tf32(acc[nb], lo, b0, b1);
+            }
+        }
+    }
+    // block reduction over the warps through the (now free) tile area, in two halves of 4 warps
+    // (4 warps x 28 taps x 16 channels = 1792 floats of the tile area)
+    __syncthreads();
+    float *red = &s.tile[0][0];
+    for (int half = 0; half < 2; ++half) {
+        if ((warp >> 2) == half) {
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int tap = 8 * nb + 2 * t + (e & 1), chn = gq + 8 * (e >> 1);
+                    if (tap < 28) red[((warp & 3) * 28 + tap) * CB_CO + chn] = acc[nb][e];
+                }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 28 * CB_CO; i += blockDim.x) {
+            float tsum = 0.f;
+            for (int ww = 0; ww < 4; ++ww) tsum += red[ww * 28 * CB_CO + i];
+            float *dst = partial + (int64_t)blockIdx.x * 28 * CB_CO + i;   // [tap][co]
+            *dst = half == 0 ? tsum : *dst + tsum;
+        }
+        __syncthreads();
+    }
+}
+
+// gw[co][tap] / gb[co] = sum over blocks of partial[block][tap][co] (fixed order)
+__global__ void cb_wgrad_reduce_kernel(const float *__restrict__ partial, int nblocks, float *__restrict__ gw, float *__restrict__ gb) {
+    // block = 32 outputs x 8 block-slices (coalesced 128-byte rows), then a fixed-order sum of the 8 slices
+    __shared__ float sl[8][32];
+    const int col = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + col;
+    float v = 0.f;
+    if (i < 28 * CB_CO)
+        for (int b = part; b < nblocks; b += 8) v += partial[(int64_t)b * 28 * CB_CO + i];
+    sl[part][col] = v;
+    __syncthreads();
+    if (part != 0 || i >= 28 * CB_CO) return;
+    v = 0.f;
+    for (int p2 = 0; p2 < 8; ++p2) v += sl[p2][col];
+    const int tap = i / CB_CO, co = i - tap * CB_CO;
+    if (tap < 27)
+        gw[co * 27 + tap] = v;
+    else
+        gb[co] = v;
+}
+
+static bool cb_geom(CbGeom &g, int B, int D, int H, int W) {
+    g.B = B; g.D = D; g.H = H; g.W = W;
+    g.segs_per_row = ceil_div(W, CB_SEG);
+    const int64_t n = (int64_t)B * D * H * g.segs_per_row;
+    g.n_vox = (int64_t)B * D * H * W;
+    if (n >= ((int64_t)1 << 31)) return false;
+    g.n_segs = (int)n;
+    return true;
+}
+
+static int cb_grid(const CbGeom &g) {
+    const int64_t want = ceil_div<int64_t>(g.n_segs, CB_WARPS);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace svr
+
+using namespace svr;
+
+extern "C" {
+
+size_t svr_conv1_bn_workspace_bytes(void) { return (size_t)sm_count() * 8 * (28 * CB_CO + 32) * sizeof(float) + 256; }
+
+int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, int B, int D, int H, int W, int Co, float eps, float momentum,
+                            float *running_mean, float *running_var, float *mean, float *invstd, void *workspace, size_t workspace_bytes,
+                            void *stream) {
+    SVR_REQUIRE(x && w && mean && invstd && workspace, "conv1_relu_bn_stats: null pointer");
+    SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
+    SVR_REQUIRE(workspace_bytes >= svr_conv1_bn_workspace_bytes(), "conv1_relu_bn_stats: workspace too small");
+    CbGeom g;
+    SVR_REQUIRE(cb_geom(g, B, D, H, W) && g.n_vox > 0, "conv1_relu_bn_stats: empty or too large grid");
+    const int grid = cb_grid(g);
+    cb_stats_kernel<<<grid, CB_WARPS * 32, 0, as_stream(stream)>>>(x, w, bias, g, (float *)workspace);
+    cb_stats_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>((const float *)workspace, grid, (double)g.n_vox, eps, momentum, running_mean,
+                                                              running_var, mean, invstd);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, const float *mean, const float *invstd, const float *gamma,
+                            const float *beta, int B, int D, int H, int W, int Co, float *y, void *stream) {
+    SVR_REQUIRE(x && w && mean && invstd && y, "conv1_relu_bn_apply: null pointer");
+    SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
+    CbGeom g;
+    SVR_REQUIRE(cb_geom(g, B, D, H, W), "conv1_relu_bn_apply: grid too large");
+    if (g.n_vox == 0) return 0;
+    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, 0, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, const float *mean, const float *invstd, const float *gamma,
+                          const float *gy, int B, int D, int H, int W, int Co, float *gw, float *gb, float *ggamma, float *gbeta,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    SVR_REQUIRE(x && w && mean && invstd && gy && gw && gb && ggamma && gbeta && workspace, "conv1_relu_bn_bwd: null pointer");
+    SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
+    SVR_REQUIRE(workspace_bytes >= svr_conv1_bn_workspace_bytes(), "conv1_relu_bn_bwd: workspace too small");
+    CbGeom g;
+    SVR_REQUIRE(cb_geom(g, B, D, H, W) && g.n_vox > 0, "conv1_relu_bn_bwd: empty or too large grid");
+    const int grid = cb_grid(g);
+    float *p32 = (float *)workspace, *p448 = p32 + (size_t)sm_count() * 8 * 32;
+    cudaStream_t st = as_stream(stream);
+    cb_bwd_reduce_kernel<<<grid, CB_WARPS * 32, 0, st>>>(x, w, bias, mean, invstd, gy, g, p32);
+    cb_bwd_finalize_kernel<<<1, 1024, 0, st>>>(p32, grid, gbeta, ggamma);
+    constexpr size_t wg_smem = sizeof(CbShared) + (size_t)CB_WARPS * CB_SEG * CB_DS * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        SVR_CUDA(cudaFuncSetAttribute(cb_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
+        attr = true;
+    }
+    cb_bwd_wgrad_kernel<<<grid, CB_WARPS * 32, wg_smem, st>>>(x, w, bias, mean, invstd, gamma, gbeta, ggamma, gy, g, (float)(1.0 / (double)g.n_vox), p448);
+    cb_wgrad_reduce_kernel<<<ceil_div(28 * CB_CO, 32), 256, 0, st>>>(p448, grid, gw, gb);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+}

@@ -82,6 +82,22 @@ class _ExtractorBase(nn.Module):
             return ops.conv1_relu_channels_last(x, conv.weight, conv.bias)
         return self.actvn(conv(x))
 
+    def _first_stage(self, conv, bn, x):
+        """bn(relu(conv(x))) of the 128-net's first stage.  Fused (csrc/conv_in_bn.cu: the 0.5 GB pre-BN activation
+        is recomputed from the one-channel input instead of stored and re-read four times) when the pair is the
+        reference's Conv3d(1,16,3,padding=1) + BatchNorm3d(16) in channels-last fp32 and no input gradient is
+        needed; otherwise the two modules run one after the other."""
+        fusable = (getattr(args, "channels_last", False) and getattr(args, "fuse_first_stage", True) and x.is_cuda and x.dtype == torch.float32
+                   and x.shape[1] == 1 and conv.out_channels == 16 and conv.kernel_size == (3, 3, 3) and conv.padding == (1, 1, 1)
+                   and conv.stride == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.weight.dtype == torch.float32
+                   and not x.requires_grad and (bn.momentum is not None or not bn.track_running_stats))
+        if fusable:
+            training = bn.training or not bn.track_running_stats
+            wants_grad = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in (conv.weight, conv.bias, bn.weight, bn.bias))
+            if training or not wants_grad:
+                return ops.conv1_relu_bn_channels_last(x, conv, bn)
+        return bn(self._first_conv_relu(conv, x))
+
     def _prep(self, x):
         """Encoder input / weights in channels_last_3d when enabled (see ``args.channels_last``)."""
         if getattr(args, "channels_last", False) and x.is_cuda:
@@ -173,7 +189,7 @@ class IFNetFeatureExtractor128(_ExtractorBase):
         self.displacments = _displacements(self.displacement)
 
     def encode(self, x):
-        net = self.conv_in_bn(self._first_conv_relu(self.conv_in, self._prep(x)))
+        net = self._first_stage(self.conv_in, self.conv_in_bn, self._prep(x))
         vols = [net]
         for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
                            (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):

@@ -215,6 +215,81 @@ def conv1_relu_channels_last(x, weight, bias):
     return _Conv1ReLU.apply(x, weight, bias)
 
 
+class _Conv1ReLUBN(torch.autograd.Function):
+    """BatchNorm3d(relu(Conv3d(1 -> 16, 3, padding=1)(x))) without ever storing the pre-BN activation
+    (csrc/conv_in_bn.cu): training mode = batch statistics (running statistics updated in place), eval mode =
+    running statistics (forward only)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, update_running, momentum, eps):
+        x0 = _dev_f32(x, "x")
+        B, _, D, H, W = x0.shape
+        Co = weight.shape[0]
+        dev = x0.device
+        w = _dev_f32(weight.detach().reshape(Co, 27), "weight")
+        b = _dev_f32(bias.detach(), "bias") if bias is not None else None
+        ga = _dev_f32(gamma.detach(), "bn.weight") if gamma is not None else None
+        be = _dev_f32(beta.detach(), "bn.bias") if beta is not None else None
+        if training:
+            mean = torch.empty((Co,), device=dev, dtype=torch.float32)
+            invstd = torch.empty((Co,), device=dev, dtype=torch.float32)
+            nbytes = _lib().svr_conv1_bn_workspace_bytes()
+            ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+            _abi.check(_lib().svr_conv1_relu_bn_stats(x0.data_ptr(), w.data_ptr(), _ptr(b), B, D, H, W, Co, float(eps), float(momentum),
+                                                      _ptr(running_mean if update_running else None),
+                                                      _ptr(running_var if update_running else None), mean.data_ptr(), invstd.data_ptr(),
+                                                      ws.data_ptr(), nbytes, _stream()), "conv1_relu_bn_stats")
+        else:
+            mean = running_mean.detach().float().contiguous()
+            invstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
+        y = torch.empty((B, D, H, W, Co), device=dev, dtype=torch.float32)
+        _abi.check(_lib().svr_conv1_relu_bn_apply(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), _ptr(be),
+                                                  B, D, H, W, Co, y.data_ptr(), _stream()), "conv1_relu_bn_apply")
+        ctx.save_for_backward(x0, w, b, ga, mean, invstd)
+        ctx.training = bool(training)
+        ctx.wshape = weight.shape
+        ctx.has = (bias is not None, gamma is not None, beta is not None)
+        return y.permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.training:
+            raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage has no eval-mode backward; use the unfused modules")
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage does not produce an input gradient")
+        x0, w, b, ga, mean, invstd = ctx.saved_tensors
+        B, _, D, H, W = x0.shape
+        Co = w.shape[0]
+        dev = x0.device
+        g = gy.permute(0, 2, 3, 4, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        g = _dev_f32(g, "grad")
+        gw = torch.empty((Co, 27), device=dev, dtype=torch.float32)
+        gb, gga, gbe = (torch.empty((Co,), device=dev, dtype=torch.float32) for _ in range(3))
+        nbytes = _lib().svr_conv1_bn_workspace_bytes()
+        ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+        _abi.check(_lib().svr_conv1_relu_bn_bwd(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), g.data_ptr(),
+                                                B, D, H, W, Co, gw.data_ptr(), gb.data_ptr(), gga.data_ptr(), gbe.data_ptr(), ws.data_ptr(),
+                                                nbytes, _stream()), "conv1_relu_bn_bwd")
+        has_b, has_g, has_be = ctx.has
+        return (None, gw.view(ctx.wshape), gb if has_b else None, gga if has_g else None, gbe if has_be else None, None, None, None, None, None,
+                None)
+
+
+def conv1_relu_bn_channels_last(x, conv, bn):
+    """bn(relu(conv(x))) for the (Conv3d(1,16,3,padding=1), BatchNorm3d(16)) pair; mirrors nn.BatchNorm3d's side
+    effects (running statistics and num_batches_tracked in training mode)."""
+    track = bn.track_running_stats and bn.running_mean is not None
+    update = bn.training and track
+    if update and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    use_batch = bn.training or not track
+    rm, rv = (bn.running_mean, bn.running_var) if track else (None, None)
+    return _Conv1ReLUBN.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, use_batch, update,
+                              bn.momentum if bn.momentum is not None else 0.0, bn.eps)
+
+
 def maxpool2_channels_last(x: torch.Tensor) -> torch.Tensor:
     return _MaxPool2CL.apply(x)
 

@@ -3,6 +3,7 @@ the unmodified reference.  Tolerances (BASELINE.json north_star): logits 1e-2 re
 tensor-core path, measured as max|d| / max|ref| (element-wise relative error is ill-defined near
 zero logits); gradients get the same per-tensor bound."""
 import numpy as np
+import copy
 import pytest
 import torch
 import torch.nn.functional as F
@@ -322,3 +323,44 @@ def test_first_conv_relu_matches_torch(co):
             assert float((p.grad - q.grad).abs().max() / q.grad.abs().max()) < 1e-4
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 20, 40), (1, 16, 16, 32), (3, 8, 9, 70)])
+def test_first_stage_fused_conv_relu_bn(shape):
+    """conv_in + ReLU + BatchNorm3d fused stage (pre-BN activation recomputed, never stored) against the two torch
+    modules in fp32 (TF32 off): output, running statistics, and the four parameter gradients.  Tolerances: 1e-4 of
+    the largest entry (summation order of the batch statistics / weight gradient only)."""
+    import svr_b200
+    from svr_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        B, D, H, W = shape
+        g = torch.Generator().manual_seed(sum(shape))
+        x = (torch.rand((B, 1, D, H, W), generator=g) < 0.3).float().cuda()
+        conv = torch.nn.Conv3d(1, 16, 3, padding=1).cuda()
+        bn = torch.nn.BatchNorm3d(16).cuda()
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(16, generator=g) + 0.5)
+            bn.bias.copy_(torch.randn(16, generator=g) * 0.1)
+        conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+        cot = torch.randn((B, 16, D, H, W), generator=g).cuda()
+        y = ops.conv1_relu_bn_channels_last(x, conv, bn)
+        (y * cot).sum().backward()
+        yr = bn_r(torch.relu(conv_r(x)))
+        (yr * cot).sum().backward()
+
+        def rel(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+        assert rel(y, yr) < 1e-4
+        assert rel(bn.running_mean, bn_r.running_mean) < 1e-5 and rel(bn.running_var, bn_r.running_var) < 1e-5
+        assert int(bn.num_batches_tracked) == int(bn_r.num_batches_tracked) == 1
+        for a, b in ((conv.weight.grad, conv_r.weight.grad), (conv.bias.grad, conv_r.bias.grad), (bn.weight.grad, bn_r.weight.grad),
+                     (bn.bias.grad, bn_r.bias.grad)):
+            assert rel(a, b) < 2e-4, rel(a, b)
+        # eval mode: running statistics, forward only
+        bn.eval(), bn_r.eval()
+        with torch.no_grad():
+            assert rel(ops.conv1_relu_bn_channels_last(x, conv, bn), bn_r(torch.relu(conv_r(x)))) < 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
