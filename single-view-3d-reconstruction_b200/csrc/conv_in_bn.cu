@@ -60,7 +60,7 @@ struct CbShared {
     ulonglong2 wt[27][CB_CO / 4];         // [tap][channel quad] as two f32x2 pairs
     float4 bs[CB_CO / 4];
     float ch[4][CB_CO];                   // per-channel constants of the pass
-    float tile[CB_WARPS][CB_TILE];
+    float tile[CB_WARPS][2][CB_TILE];     // double-buffered: the next segment's rows arrive by cp.async during the math
 };
 
 __device__ __forceinline__ void cb_load_weights(CbShared &s, const float *__restrict__ w, const float *__restrict__ bias) {
@@ -70,36 +70,85 @@ __device__ __forceinline__ void cb_load_weights(CbShared &s, const float *__rest
     }
     if (threadIdx.x < CB_CO) reinterpret_cast<float *>(s.bs)[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = lane; e < CB_RS; e += 32) {
-        s.tile[warp][9 * CB_RS + e] = 1.f;
-        s.tile[warp][10 * CB_RS + e] = 0.f;
-    }
+    for (int e = lane; e < CB_RS; e += 32)
+        for (int b = 0; b < 2; ++b) {
+            s.tile[warp][b][9 * CB_RS + e] = 1.f;
+            s.tile[warp][b][10 * CB_RS + e] = 0.f;
+        }
 }
 
-// segment -> voxel index of its first voxel and x0; stages the 3x3 rows x0-1 .. x0+64 of x in the warp's tile
-// (tile[r][e] = x at x0 - 1 + e)
-__device__ __forceinline__ int64_t cb_stage(const CbGeom &g, const float *__restrict__ x, int seg, int lane, float *tile, int &x0) {
+__device__ __forceinline__ void cb_cp4(uint32_t dst_smem, const float *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cb_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cb_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct CbSeg {
+    int64_t p0;   // voxel index of the segment's first voxel
+    int x0;
+};
+
+// Issues the asynchronous copies of the 3x3 rows x0-1 .. x0+64 of x into `tile` (tile[r][e] = x at x0 - 1 + e, zero
+// outside the volume) and commits them as one cp.async group.  The caller must have passed a __syncwarp since the
+// last reader of `tile`.
+__device__ __forceinline__ CbSeg cb_issue(const CbGeom &g, const float *__restrict__ x, int seg, int lane, float *tile) {
     const int row = seg / g.segs_per_row;
-    x0 = (seg - row * g.segs_per_row) * CB_SEG;
+    CbSeg sg;
+    sg.x0 = (seg - row * g.segs_per_row) * CB_SEG;
     const int yy = row % g.H, r2 = row / g.H;
     const int zz = r2 % g.D, b = r2 / g.D;
     const int64_t base = (((int64_t)b * g.D + zz) * g.H + yy) * g.W;
-    __syncwarp();                                     // the previous segment's readers are done
+    sg.p0 = base + sg.x0;
+    const int xa = sg.x0 - 1 + lane;
+    const uint32_t sz_a = (xa >= 0 && xa < g.W) ? 4u : 0u, sz_b = (xa + 32 < g.W) ? 4u : 0u, sz_c = (xa + 64 < g.W) ? 4u : 0u;
+    const float *src0 = x + base + xa;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(tile + lane);
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
         const int z = zz + r / 3 - 1, yq = yy + r % 3 - 1;
-        const bool row_ok = z >= 0 && z < g.D && yq >= 0 && yq < g.H;
-        const float *src = x + base + ((int64_t)(r / 3 - 1) * g.H + (r % 3 - 1)) * g.W;
-        const int xa = x0 - 1 + lane, xb = xa + 32;
-        tile[r * CB_RS + lane] = (row_ok && xa >= 0 && xa < g.W) ? __ldg(src + xa) : 0.f;
-        tile[r * CB_RS + 32 + lane] = (row_ok && xb < g.W) ? __ldg(src + xb) : 0.f;
-        if (lane < 2) {
-            const int xc = x0 + 63 + lane;
-            tile[r * CB_RS + 64 + lane] = (row_ok && xc < g.W) ? __ldg(src + xc) : 0.f;
+        if (z >= 0 && z < g.D && yq >= 0 && yq < g.H) {          // warp-uniform
+            const float *src = src0 + ((r / 3 - 1) * g.H + (r % 3 - 1)) * g.W;
+            cb_cp4(dst0 + r * CB_RS * 4, src, sz_a);
+            cb_cp4(dst0 + r * CB_RS * 4 + 128, src + 32, sz_b);
+            if (lane < 2) cb_cp4(dst0 + r * CB_RS * 4 + 256, src + 64, sz_c);
+        } else {
+            tile[r * CB_RS + lane] = 0.f;
+            tile[r * CB_RS + 32 + lane] = 0.f;
+            if (lane < 2) tile[r * CB_RS + 64 + lane] = 0.f;
         }
     }
-    __syncwarp();
-    return base + x0;
+    cb_commit();
+    return sg;
+}
+
+// Segment loop of every pass: the rows of segment i+1 are in flight while `body(tile, segment)` works on segment i.
+template <typename Body>
+__device__ __forceinline__ void cb_for_each_segment(const CbGeom &g, const float *__restrict__ x, CbShared &s, Body body) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x * CB_WARPS;
+    int seg = blockIdx.x * CB_WARPS + warp, buf = 0;
+    if (seg >= g.n_segs) return;
+    CbSeg cur = cb_issue(g, x, seg, lane, s.tile[warp][0]);
+    while (true) {
+        const int next = seg + stride;
+        CbSeg nxt = cur;
+        if (next < g.n_segs) {
+            nxt = cb_issue(g, x, next, lane, s.tile[warp][buf ^ 1]);
+            cb_wait<1>();
+        } else {
+            cb_wait<0>();
+        }
+        __syncwarp();                       // every lane's copies of the current tile have landed
+        body(s.tile[warp][buf], cur);
+        __syncwarp();                       // readers done before the tile is refilled (two iterations ahead)
+        if (next >= g.n_segs) break;
+        seg = next;
+        cur = nxt;
+        buf ^= 1;
+    }
 }
 
 // a[j][c] = relu(bias[c] + sum_tap w[c][tap] * x[voxel_j + tap]) for the lane's voxels lane and lane+32 (fixed
@@ -165,30 +214,28 @@ __device__ __forceinline__ void cb_block_reduce32(float (&s1)[CB_CO], float (&s2
 // ---- forward pass 1: batch statistics of a -------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_WARPS * 32) cb_stats_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                                  const float *__restrict__ bias, const CbGeom g, float *__restrict__ partial) {
-    __shared__ CbShared s;
+    extern __shared__ __align__(16) uint8_t cb_dyn[];
+    CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
     cb_load_weights(s, w, bias);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *tile = s.tile[warp];
+    const int lane = threadIdx.x & 31;
     float s1[CB_CO], s2[CB_CO];
 #pragma unroll
     for (int c = 0; c < CB_CO; ++c) s1[c] = s2[c] = 0.f;
-    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
-        int x0;
-        cb_stage(g, x, seg, lane, tile, x0);
+    cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {
         float a[2][CB_CO];
         cb_conv_relu(s, tile, lane, a);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            if (x0 + lane + 32 * j < g.W) {
+            if (sg.x0 + lane + 32 * j < g.W) {
 #pragma unroll
                 for (int c = 0; c < CB_CO; ++c) {
                     s1[c] += a[j][c];
                     s2[c] = fmaf(a[j][c], a[j][c], s2[c]);
                 }
             }
-    }
-    cb_block_reduce32(s1, s2, &s.tile[0][0], partial);   // the tiles are free after the loop (barrier inside)
+    });
+    cb_block_reduce32(s1, s2, &s.tile[0][0][0], partial);   // the tiles are free after the loop (barrier inside)
 }
 
 // mean / inverse standard deviation from the block partials (double), running statistics updated like
@@ -226,7 +273,8 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__
                                                                  const float *__restrict__ bias, const float *__restrict__ mean,
                                                                  const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                                  const float *__restrict__ beta, const CbGeom g, float *__restrict__ y) {
-    __shared__ CbShared s;
+    extern __shared__ __align__(16) uint8_t cb_dyn[];
+    CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
     cb_load_weights(s, w, bias);
     if (threadIdx.x < CB_CO) {
         const float sc = (gamma ? gamma[threadIdx.x] : 1.f) * invstd[threadIdx.x];
@@ -234,24 +282,21 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__
         s.ch[1][threadIdx.x] = (beta ? beta[threadIdx.x] : 0.f) - mean[threadIdx.x] * sc;
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *tile = s.tile[warp];
-    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
-        int x0;
-        const int64_t p0 = cb_stage(g, x, seg, lane, tile, x0);
+    const int lane = threadIdx.x & 31;
+    cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {
         float a[2][CB_CO];
         cb_conv_relu(s, tile, lane, a);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            if (x0 + lane + 32 * j < g.W) {
-                float4 *dst = reinterpret_cast<float4 *>(y + (p0 + lane + 32 * j) * CB_CO);
+            if (sg.x0 + lane + 32 * j < g.W) {
+                float4 *dst = reinterpret_cast<float4 *>(y + (sg.p0 + lane + 32 * j) * CB_CO);
 #pragma unroll
                 for (int c = 0; c < CB_CO / 4; ++c)
                     dst[c] = make_float4(fmaf(a[j][4 * c], s.ch[0][4 * c], s.ch[1][4 * c]), fmaf(a[j][4 * c + 1], s.ch[0][4 * c + 1], s.ch[1][4 * c + 1]),
                                          fmaf(a[j][4 * c + 2], s.ch[0][4 * c + 2], s.ch[1][4 * c + 2]),
                                          fmaf(a[j][4 * c + 3], s.ch[0][4 * c + 3], s.ch[1][4 * c + 3]));
             }
-    }
+    });
 }
 
 // ---- backward pass 1: sum gy, sum gy * xhat ---------------------------------------------------------------------
@@ -259,26 +304,24 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_bwd_reduce_kernel(const floa
                                                                       const float *__restrict__ bias, const float *__restrict__ mean,
                                                                       const float *__restrict__ invstd, const float *__restrict__ gy,
                                                                       const CbGeom g, float *__restrict__ partial) {
-    __shared__ CbShared s;
+    extern __shared__ __align__(16) uint8_t cb_dyn[];
+    CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
     cb_load_weights(s, w, bias);
     if (threadIdx.x < CB_CO) {
         s.ch[0][threadIdx.x] = mean[threadIdx.x];
         s.ch[1][threadIdx.x] = invstd[threadIdx.x];
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *tile = s.tile[warp];
+    const int lane = threadIdx.x & 31;
     float s1[CB_CO], s2[CB_CO];
 #pragma unroll
     for (int c = 0; c < CB_CO; ++c) s1[c] = s2[c] = 0.f;
-    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
-        int x0;
-        const int64_t p0 = cb_stage(g, x, seg, lane, tile, x0);
+    cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {
         float4 gq[2][CB_CO / 4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const bool ok = x0 + lane + 32 * j < g.W;
-            const float4 *src = reinterpret_cast<const float4 *>(gy + (p0 + lane + 32 * j) * CB_CO);
+            const bool ok = sg.x0 + lane + 32 * j < g.W;
+            const float4 *src = reinterpret_cast<const float4 *>(gy + (sg.p0 + lane + 32 * j) * CB_CO);
 #pragma unroll
             for (int c = 0; c < CB_CO / 4; ++c) gq[j][c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -297,8 +340,8 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_bwd_reduce_kernel(const floa
                     s2[ch] = fmaf(gv[e], xh, s2[ch]);
                 }
             }
-    }
-    cb_block_reduce32(s1, s2, &s.tile[0][0], partial);
+    });
+    cb_block_reduce32(s1, s2, &s.tile[0][0][0], partial);
 }
 
 // ggamma = sum gy * xhat, gbeta = sum gy (double reduce of the block partials)
@@ -340,7 +383,6 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *tile = s.tile[warp];
     float *dz = park + warp * (CB_SEG * CB_DS);
     // MMA roles (m16n8k8: M = channel, N = tap, K = voxel): gq = lane / 4, t = lane % 4.
     //   A (dz^T)  a0 (ch gq, vox t)  a1 (ch gq+8, vox t)  a2 (ch gq, vox t+4)  a3 (ch gq+8, vox t+4)
@@ -358,14 +400,13 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
     for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
-    for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
-        int x0;
-        const int64_t p0 = cb_stage(g, x, seg, lane, tile, x0);   // leading __syncwarp: last segment's parked rows are consumed
+    cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {   // __syncwarp after each body: parked rows consumed
+        const int x0 = sg.x0;
         float4 gv4[2][CB_CO / 4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const bool ok = x0 + lane + 32 * j < g.W;
-            const float4 *src = reinterpret_cast<const float4 *>(gy + (p0 + lane + 32 * j) * CB_CO);
+            const float4 *src = reinterpret_cast<const float4 *>(gy + (sg.p0 + lane + 32 * j) * CB_CO);
 #pragma unroll
             for (int c = 0; c < CB_CO / 4; ++c) gv4[j][c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -406,11 +447,11 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
                 mma_tf32(acc[nb], lo, b0, b1);
             }
         }
-    }
+    });
     // block reduction over the warps through the (now free) tile area, in two halves of 4 warps
     // (4 warps x 28 taps x 16 channels = 1792 floats of the tile area)
     __syncthreads();
-    float *red = &s.tile[0][0];
+    float *red = &s.tile[0][0][0];
     for (int half = 0; half < 2; ++half) {
         if ((warp >> 2) == half) {
 #pragma unroll
@@ -463,6 +504,21 @@ static bool cb_geom(CbGeom &g, int B, int D, int H, int W) {
     return true;
 }
 
+constexpr size_t CB_SMEM = sizeof(CbShared);
+constexpr size_t CB_SMEM_WGRAD = sizeof(CbShared) + (size_t)CB_WARPS * CB_SEG * CB_DS * sizeof(float);
+
+static int cb_attrs() {
+    static bool done = false;
+    if (!done) {
+        SVR_CUDA(cudaFuncSetAttribute(cb_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
+        SVR_CUDA(cudaFuncSetAttribute(cb_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
+        SVR_CUDA(cudaFuncSetAttribute(cb_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
+        SVR_CUDA(cudaFuncSetAttribute(cb_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM_WGRAD));
+        done = true;
+    }
+    return 0;
+}
+
 static int cb_grid(const CbGeom &g) {
     const int64_t want = ceil_div<int64_t>(g.n_segs, CB_WARPS);
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -486,7 +542,8 @@ int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, i
     CbGeom g;
     SVR_REQUIRE(cb_geom(g, B, D, H, W) && g.n_vox > 0, "conv1_relu_bn_stats: empty or too large grid");
     const int grid = cb_grid(g);
-    cb_stats_kernel<<<grid, CB_WARPS * 32, 0, as_stream(stream)>>>(x, w, bias, g, (float *)workspace);
+    if (int rc = cb_attrs()) return rc;
+    cb_stats_kernel<<<grid, CB_WARPS * 32, CB_SMEM, as_stream(stream)>>>(x, w, bias, g, (float *)workspace);
     cb_stats_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>((const float *)workspace, grid, (double)g.n_vox, eps, momentum, running_mean,
                                                               running_var, mean, invstd);
     SVR_LAUNCH_CHECK();
@@ -500,7 +557,8 @@ int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, c
     CbGeom g;
     SVR_REQUIRE(cb_geom(g, B, D, H, W), "conv1_relu_bn_apply: grid too large");
     if (g.n_vox == 0) return 0;
-    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, 0, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y);
+    if (int rc = cb_attrs()) return rc;
+    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, CB_SMEM, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y);
     SVR_LAUNCH_CHECK();
     return 0;
 }
@@ -516,15 +574,10 @@ int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, con
     const int grid = cb_grid(g);
     float *p32 = (float *)workspace, *p448 = p32 + (size_t)sm_count() * 8 * 32;
     cudaStream_t st = as_stream(stream);
-    cb_bwd_reduce_kernel<<<grid, CB_WARPS * 32, 0, st>>>(x, w, bias, mean, invstd, gy, g, p32);
+    if (int rc = cb_attrs()) return rc;
+    cb_bwd_reduce_kernel<<<grid, CB_WARPS * 32, CB_SMEM, st>>>(x, w, bias, mean, invstd, gy, g, p32);
     cb_bwd_finalize_kernel<<<1, 1024, 0, st>>>(p32, grid, gbeta, ggamma);
-    constexpr size_t wg_smem = sizeof(CbShared) + (size_t)CB_WARPS * CB_SEG * CB_DS * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        SVR_CUDA(cudaFuncSetAttribute(cb_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
-        attr = true;
-    }
-    cb_bwd_wgrad_kernel<<<grid, CB_WARPS * 32, wg_smem, st>>>(x, w, bias, mean, invstd, gamma, gbeta, ggamma, gy, g, (float)(1.0 / (double)g.n_vox), p448);
+    cb_bwd_wgrad_kernel<<<grid, CB_WARPS * 32, CB_SMEM_WGRAD, st>>>(x, w, bias, mean, invstd, gamma, gbeta, ggamma, gy, g, (float)(1.0 / (double)g.n_vox), p448);
     cb_wgrad_reduce_kernel<<<ceil_div(28 * CB_CO, 32), 256, 0, st>>>(p448, grid, gw, gb);
     SVR_LAUNCH_CHECK();
     return 0;
