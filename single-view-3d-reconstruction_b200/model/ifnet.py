@@ -82,6 +82,15 @@ class _ExtractorBase(nn.Module):
             return ops.conv1_relu_channels_last(x, conv.weight, conv.bias)
         return self.actvn(conv(x))
 
+    def _conv(self, conv, x):
+        """conv(x); for the large channels-last layers (>= 2^20 input voxels) the backward kernels run on bf16
+        operands (``args.bf16_conv_backward``, see ops._ConvBf16Backward) while the forward stays fp32/TF32."""
+        if (getattr(args, "bf16_conv_backward", True) and getattr(args, "channels_last", False) and x.is_cuda and x.dtype == torch.float32
+                and torch.is_grad_enabled() and conv.weight.requires_grad and conv.padding_mode == "zeros"
+                and x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= (1 << 20)):
+            return ops.conv3d_bf16_backward(x, conv)
+        return conv(x)
+
     def _first_stage(self, conv, bn, x):
         """bn(relu(conv(x))) of the 128-net's first stage.  Fused (csrc/conv_in_bn.cu: the 0.5 GB pre-BN activation
         is recomputed from the one-channel input instead of stored and re-read four times) when the pair is the
@@ -154,8 +163,8 @@ class IFNetFeatureExtractor(_ExtractorBase):
                   (self.conv_3, self.conv_3_1, self.conv3_1_bn))
         vols, net = [], self._prep(x)
         for i, (ca, cb, bn) in enumerate(stages):
-            first = self._first_conv_relu(ca, net) if i == 0 else self.actvn(ca(net))
-            net = bn(self.actvn(cb(first)))
+            first = self._first_conv_relu(ca, net) if i == 0 else self.actvn(self._conv(ca, net))
+            net = bn(self.actvn(self._conv(cb, first)))
             vols.append(net)
             if i + 1 < len(stages):
                 net = self._pool(net)
@@ -194,7 +203,7 @@ class IFNetFeatureExtractor128(_ExtractorBase):
         for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
                            (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):
             net = self._pool(net)
-            net = bn(self.actvn(cb(self.actvn(ca(net)))))
+            net = bn(self.actvn(self._conv(cb, self.actvn(self._conv(ca, net)))))
             vols.append(net)
         return vols
 

@@ -364,3 +364,28 @@ def test_first_stage_fused_conv_relu_bn(shape):
             assert rel(ops.conv1_relu_bn_channels_last(x, conv, bn), bn_r(torch.relu(conv_r(x)))) < 1e-5
     finally:
         torch.backends.cudnn.allow_tf32 = True
+
+
+def test_conv3d_bf16_backward_matches_fp32():
+    """Encoder convolution with bf16-operand backward kernels: forward identical to nn.Conv3d, gradients within
+    1e-2 relative L2 of the fp32 (TF32 off) gradients (bf16 rounding of activation and incoming gradient)."""
+    from svr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    conv = torch.nn.Conv3d(16, 32, 3, padding=1).cuda().to(memory_format=torch.channels_last_3d)
+    ref = copy.deepcopy(conv)
+    x = torch.randn((2, 16, 24, 24, 24), generator=g).cuda().contiguous(memory_format=torch.channels_last_3d)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    cot = torch.randn((2, 32, 24, 24, 24), generator=g).cuda()
+    y = ops.conv3d_bf16_backward(xa, conv)
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        yr = ref(xb)
+        (yr * cot).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    (y * cot).sum().backward()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(y, yr) < 2e-3                      # TF32 forward
+    assert rel(xa.grad, xb.grad) < 1e-2
+    assert rel(conv.weight.grad, ref.weight.grad) < 1e-2
+    assert rel(conv.bias.grad, ref.bias.grad) < 1e-5
