@@ -146,7 +146,7 @@ int svr_conv1_relu_bwd(const float *x, const float *y, const float *gy, const fl
 /* nn.MaxPool3d(2) of the encoder (ifnet.py:133,169-190) on channels-last (NDHWC) fp32 activations,
  * forward (+ packed per-channel argmax, one byte per output element, 4 per uint32) and backward.
  * Keeps the torch/cuDNN encoder channels-last end to end (torch's max_pool3d would make an NCDHW
- * copy).  torch semantics: floor output size, first maximum wins, NaN propagates.  C %% 4 == 0.  */
+ * copy).  torch semantics: floor output size, first maximum wins, NaN propagates.  C % 4 == 0.  */
 int svr_maxpool2_cl_fwd(const float *in, int B, int D, int H, int W, int C, float *out, uint32_t *idx, void *stream);
 int svr_maxpool2_cl_bwd(const float *gout, const uint32_t *idx, int B, int D, int H, int W, int C, float *gin, void *stream);
 
@@ -223,6 +223,16 @@ int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, c
 int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, const float *mean, const float *invstd,
                           const float *gamma, const float *gy, int B, int D, int H, int W, int Co, float *gw, float *gb,
                           float *ggamma, float *gbeta, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Elementwise glue of the encoder's Conv3d -> ReLU layers (ifnet.py:127-135,165-183 `self.actvn(self.conv_x(net))`),
+ * channels-last fp32 activations viewed as (rows = B*D*H*W, C), C % 4 == 0 and 256 % (C/4) == 0.
+ *   svr_bias_relu_cl : y <- max(y + bias, 0) in place (bias nullable).
+ *   svr_relu_bwd_cl  : g = gy * [y > 0] as fp32 (g_f32, nullable) and/or bf16 (g_bf16, nullable); gbias[c] = sum_rows g
+ *                      (nullable) from the same pass.                                                             */
+int svr_bias_relu_cl(float *y, const float *bias, int64_t rows, int C, void *stream);
+size_t svr_relu_bwd_cl_workspace_bytes(int C);
+int svr_relu_bwd_cl(const float *gy, const float *y, int64_t rows, int C, float *g_f32, uint16_t *g_bf16, float *gbias,
+                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* Fused decoder backward-data chain (Conv1d backward of ifnet.py:55-58, hidden size 256):
  *   dz1 = (dz2 . W2) * [h1 > 0],  dz0 = (dz1 . W1) * [h0 > 0],  dfeat = dz0 . W0'   (all bf16, row-major)

@@ -91,6 +91,17 @@ class _ExtractorBase(nn.Module):
             return ops.conv3d_bf16_backward(x, conv)
         return conv(x)
 
+    def _conv_relu(self, conv, x):
+        """self.actvn(conv(x)).  Channels-last fp32 on the GPU: cuDNN convolution + one fused bias/ReLU pass forward and
+        one fused mask / bias-gradient / cast pass backward (ops._ConvBiasReLU); otherwise the two modules."""
+        co = conv.out_channels
+        if (getattr(args, "channels_last", False) and getattr(args, "fuse_conv_relu", True) and x.is_cuda and x.dtype == torch.float32
+                and conv.weight.dtype == torch.float32 and conv.padding_mode == "zeros" and co % 4 == 0 and 256 % (co // 4) == 0
+                and x.is_contiguous(memory_format=torch.channels_last_3d)):
+            big = x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= (1 << 20)
+            return ops.conv3d_bias_relu(x, conv, bool(getattr(args, "bf16_conv_backward", True) and big))
+        return self.actvn(self._conv(conv, x))
+
     def _first_stage(self, conv, bn, x):
         """bn(relu(conv(x))) of the 128-net's first stage.  Fused (csrc/conv_in_bn.cu: the 0.5 GB pre-BN activation
         is recomputed from the one-channel input instead of stored and re-read four times) when the pair is the
@@ -163,8 +174,8 @@ class IFNetFeatureExtractor(_ExtractorBase):
                   (self.conv_3, self.conv_3_1, self.conv3_1_bn))
         vols, net = [], self._prep(x)
         for i, (ca, cb, bn) in enumerate(stages):
-            first = self._first_conv_relu(ca, net) if i == 0 else self.actvn(self._conv(ca, net))
-            net = bn(self.actvn(self._conv(cb, first)))
+            first = self._first_conv_relu(ca, net) if i == 0 else self._conv_relu(ca, net)
+            net = bn(self._conv_relu(cb, first))
             vols.append(net)
             if i + 1 < len(stages):
                 net = self._pool(net)
@@ -203,7 +214,7 @@ class IFNetFeatureExtractor128(_ExtractorBase):
         for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
                            (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):
             net = self._pool(net)
-            net = bn(self.actvn(self._conv(cb, self.actvn(self._conv(ca, net)))))
+            net = bn(self._conv_relu(cb, self._conv_relu(ca, net)))
             vols.append(net)
         return vols
 

@@ -317,6 +317,59 @@ class _ConvBf16Backward(torch.autograd.Function):
         return (gx.float() if gx is not None else None, gw.to(weight.dtype) if gw is not None else None, gb, None, None, None, None)
 
 
+class _ConvBiasReLU(torch.autograd.Function):
+    """relu(Conv3d(x)) for channels-last fp32 activations: cuDNN convolution without bias, then ONE in-place
+    bias+ReLU pass (csrc/encoder_glue.cu); the backward masks the gradient, sums the bias gradient and emits the
+    bf16 (large layers) or fp32 operand of the convolution backward kernels in ONE pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, bf16_backward):
+        cl = torch.channels_last_3d
+        y = torch.nn.functional.conv3d(x, weight, None, stride, padding, dilation, groups)
+        if not y.is_contiguous(memory_format=cl):
+            y = y.contiguous(memory_format=cl)
+        Co = y.shape[1]
+        rows = y.numel() // Co
+        _abi.check(_lib().svr_bias_relu_cl(y.data_ptr(), _ptr(bias.detach() if bias is not None else None), rows, Co, _stream()), "bias_relu_cl")
+        xs = x.detach()
+        ctx.save_for_backward(xs.to(torch.bfloat16).contiguous(memory_format=cl) if bf16_backward else xs, weight, y)
+        ctx.conf = (stride, padding, dilation, groups, bias is not None, bool(bf16_backward))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xs, weight, y = ctx.saved_tensors
+        stride, padding, dilation, groups, has_bias, bf16_backward = ctx.conf
+        cl = torch.channels_last_3d
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        if not gy.is_contiguous(memory_format=cl):   # the kernel reads (rows, C): NDHWC storage
+            gy = gy.contiguous(memory_format=cl)
+        Co = y.shape[1]
+        rows = y.numel() // Co
+        dev = y.device
+        g = torch.empty_like(y, dtype=torch.bfloat16 if bf16_backward else torch.float32, memory_format=cl)
+        gb = torch.empty((Co,), device=dev, dtype=torch.float32) if has_bias else None
+        nbytes = _lib().svr_relu_bwd_cl_workspace_bytes(Co)
+        ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+        _abi.check(_lib().svr_relu_bwd_cl(gy.data_ptr(), y.data_ptr(), rows, Co, None if bf16_backward else g.data_ptr(),
+                                          g.data_ptr() if bf16_backward else None, _ptr(gb), ws.data_ptr(), nbytes, _stream()), "relu_bwd_cl")
+        w = weight.detach()
+        if bf16_backward:
+            w = w.to(torch.bfloat16).contiguous(memory_format=cl)
+        gx, gw, _ = torch.ops.aten.convolution_backward(g, xs, w, None, list(stride), list(padding), list(dilation), False, [0, 0, 0], groups,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        if gx is not None and gx.dtype != torch.float32:
+            gx = gx.float()
+        if gw is not None and gw.dtype != weight.dtype:
+            gw = gw.to(weight.dtype)
+        return gx, gw, gb, None, None, None, None, None
+
+
+def conv3d_bias_relu(x, conv, bf16_backward):
+    return _ConvBiasReLU.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, bf16_backward)
+
+
 def conv3d_bf16_backward(x, conv):
     return _ConvBf16Backward.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 

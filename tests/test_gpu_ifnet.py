@@ -389,3 +389,29 @@ def test_conv3d_bf16_backward_matches_fp32():
     assert rel(xa.grad, xb.grad) < 1e-2
     assert rel(conv.weight.grad, ref.weight.grad) < 1e-2
     assert rel(conv.bias.grad, ref.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("bf16_backward", [False, True])
+def test_conv_bias_relu_fused(bf16_backward):
+    """relu(conv(x)) with the fused bias/ReLU forward pass and mask / bias-gradient / cast backward pass against the
+    torch modules run with the same (TF32) cuDNN forward, so that both sides take the same ReLU decisions.
+    fp32-operand backward: 2e-3 relative L2; bf16-operand backward: 2e-2 (bf16 rounding of gradient, activation
+    and weight; measured 1.3e-2)."""
+    from svr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    conv = torch.nn.Conv3d(32, 64, 3, padding=1).cuda().to(memory_format=torch.channels_last_3d)
+    ref = copy.deepcopy(conv)
+    x = torch.randn((2, 32, 12, 10, 14), generator=g).cuda().contiguous(memory_format=torch.channels_last_3d)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    cot = torch.randn((2, 64, 12, 10, 14), generator=g).cuda()
+    y = ops.conv3d_bias_relu(xa, conv, bf16_backward)
+    yr = torch.relu(ref(xb))
+    (yr * cot).sum().backward()
+    (y * cot).sum().backward()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    tol = 2e-2 if bf16_backward else 2e-3
+    assert rel(y, yr) < 1e-5
+    assert float(((y > 0) != (yr > 0)).float().mean()) < 1e-4
+    assert rel(xa.grad, xb.grad) < tol, rel(xa.grad, xb.grad)
+    assert rel(conv.weight.grad, ref.weight.grad) < tol, rel(conv.weight.grad, ref.weight.grad)
+    assert rel(conv.bias.grad, ref.bias.grad) < 2e-3
