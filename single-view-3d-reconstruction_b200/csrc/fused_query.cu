@@ -29,7 +29,8 @@ constexpr int FQ_B_BYTES = FQ_HID * 128;         // 32 KB: 256 rows x 64 bf16
 constexpr int FQ_H_BYTES = FQ_TILE * FQ_HID * 2; // 64 KB: 4 K-chunks of 16 KB
 constexpr int FQ_EPI_WARPS = 4;
 constexpr int fq_threads(int gather_warps) { return (FQ_EPI_WARPS + 2 + gather_warps) * 32; }   // 448 for 8 gather warps
-constexpr int FQ_SMEM = 1024 + FQ_NA * FQ_A_BYTES + FQ_NB * FQ_B_BYTES + FQ_H_BYTES + 2 * FQ_TILE * 16 + 512;
+constexpr int FQ_UTAB = 512;                     // unit table entries (KP <= 4096)
+constexpr int FQ_SMEM = 1024 + FQ_NA * FQ_A_BYTES + FQ_NB * FQ_B_BYTES + FQ_H_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4;
 
 struct FqVols {
     const __nv_bfloat16 *v[SVR_MAX_LEVELS];
@@ -101,6 +102,7 @@ struct FqSmem {
     float4 *pts;                 // [2][128] : (px,py,pz, scene as int bits)
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *h_ready;
     uint32_t *tmem_ptr;
+    uint32_t *utab;              // [FQ_UTAB] packed decode_unit results
 };
 
 __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw) {
@@ -118,6 +120,7 @@ __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw) {
     s.acc_full = s.b_empty + FQ_NB;   // [2]
     s.h_ready = s.acc_full + 2;       // [1]
     s.tmem_ptr = (uint32_t *)(s.h_ready + 1);
+    s.utab = (uint32_t *)((uint8_t *)bars + 512);
     return s;
 }
 
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc(s.tmem_ptr, 512);
+    for (int u = threadIdx.x; u < KC0 * 8; u += blockDim.x) s.utab[u] = pack_unit(p.P, u);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 const int st = gc % FQ_NA;
                 const int u = kc * 8 + unit_in_chunk;
                 UnitCtx uc;
-                make_unit_ctx(p.P, u, p.vols.v, uc);
+                make_unit_ctx_packed(p.P, s.utab[u], p.vols.v, uc);
                 mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
                 uint8_t *a_st = s.a + st * FQ_A_BYTES;
 #pragma unroll 2
@@ -183,13 +187,24 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     const float4 q = pts_s[r];
                     const int scene = __float_as_int(q.w);
                     uint4 val = make_uint4(0, 0, 0, 0);
-                    if (uc.real && scene >= 0) {
-                        if (uc.level > 0) {
-                            val = gather_unit_fast(uc, p.P.align, q.x, q.y, q.z, scene);
-                        } else {
+                    if (kc == 0) {
+                        // Unit 0 is the level-0 unit: 7 stencil samples of the fp32 input grid (56 scalar loads).  Left to
+                        // the one lane that owns unit 0 it made chunk 0 cost about a fifth of a tile's gather time
+                        // (1 chunk of 41); instead lane j of the point's 8-lane group takes sample j and lane 0 collects.
+                        float smp = 0.f;
+                        if (scene >= 0 && unit_in_chunk < 7) {
                             const float *x0b = p.x0 + (int64_t)scene * p.P.D[0] * p.P.H[0] * p.P.W[0];
-                            val = gather_unit_decoded(p.P, 0, 0, 0, q.x, q.y, q.z, x0b, nullptr);
+                            smp = level0_sample(p.P, unit_in_chunk, q.x, q.y, q.z, x0b);
                         }
+                        float v8[8];
+#pragma unroll
+                        for (int dd = 0; dd < 8; ++dd) v8[dd] = __shfl_sync(0xffffffffu, smp, (lane & 24) + dd);
+                        if (unit_in_chunk == 0)
+                            val = float8_to_bf16(v8);
+                        else if (uc.real && uc.level > 0 && scene >= 0)
+                            val = gather_unit_fast(uc, p.P.align, q.x, q.y, q.z, scene);
+                    } else if (uc.real && scene >= 0) {
+                        val = gather_unit_fast(uc, p.P.align, q.x, q.y, q.z, scene);
                     }
                     *reinterpret_cast<uint4 *>(a_st + swz128(r, unit_in_chunk)) = val;
                     if (p.save_feat) {
@@ -884,6 +899,7 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
     SVR_REQUIRE(w->h0 == FQ_HID && w->h1 == FQ_HID && w->h2 == FQ_HID, "fused query supports hidden size 256 only (got %d/%d/%d)",
                 w->h0, w->h1, w->h2);
     SVR_REQUIRE(w->w0p && w->w1 && w->w2 && w->b0 && w->b1 && w->b2 && w->wout && w->bout, "fused query: null weight pointer");
+    SVR_REQUIRE(p.P.kp / 8 <= FQ_UTAB, "fused query: feature row of %d columns exceeds the unit table (%d columns)", p.P.kp, FQ_UTAB * 8);
     for (int l = 0; l < SVR_MAX_LEVELS; ++l) {
         p.vols.v[l] = (l >= 1 && l < p.P.n_levels) ? (const __nv_bfloat16 *)vols_host[l] : nullptr;
         SVR_REQUIRE(!(l >= 1 && l < p.P.n_levels) || p.vols.v[l], "fused query: volume of level %d is null", l);
