@@ -88,7 +88,7 @@ __device__ __forceinline__ void cb_wait() {
 
 struct CbSeg {
     int64_t p0;   // voxel index of the segment's first voxel
-    int x0;
+    int x0, yy, zz, b;
 };
 
 // Issues the asynchronous copies of the 3x3 rows x0-1 .. x0+64 of x into `tile` (tile[r][e] = x at x0 - 1 + e, zero
@@ -102,6 +102,9 @@ __device__ __forceinline__ CbSeg cb_issue(const CbGeom &g, const float *__restri
     const int zz = r2 % g.D, b = r2 / g.D;
     const int64_t base = (((int64_t)b * g.D + zz) * g.H + yy) * g.W;
     sg.p0 = base + sg.x0;
+    sg.yy = yy;
+    sg.zz = zz;
+    sg.b = b;
     const int xa = sg.x0 - 1 + lane;
     const uint32_t sz_a = (xa >= 0 && xa < g.W) ? 4u : 0u, sz_b = (xa + 32 < g.W) ? 4u : 0u, sz_c = (xa + 64 < g.W) ? 4u : 0u;
     const float *src0 = x + base + xa;
@@ -182,6 +185,33 @@ __device__ __forceinline__ void cb_conv_relu(const CbShared &s, const float *til
             a[j][2 * c] = fmaxf(lo, 0.f);
             a[j][2 * c + 1] = fmaxf(hi, 0.f);
         }
+}
+
+// Incoming gradient of y at voxel x0 + lane + 32 j of the segment, channel quad c: the gradient that reaches y directly
+// (gy, nullable) plus the share routed through the fused nn.MaxPool3d(2) (g_pool: gradient of the pooled tensor,
+// pool_idx: the winner codes svr_maxpool2_cl_fwd wrote, both nullable) -- the pooling backward and the sum of the
+// two gradient branches never touch memory.
+struct CbGrad {
+    const float *gy;
+    const float *g_pool;
+    const uint32_t *pool_idx;
+};
+__device__ __forceinline__ float4 cb_load_grad(const CbGrad &gr, const CbGeom &g, const CbSeg &sg, int xq, int c) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xq >= g.W) return v;
+    if (gr.gy) v = __ldg(reinterpret_cast<const float4 *>(gr.gy + (sg.p0 + (xq - sg.x0)) * CB_CO) + c);
+    const int Do = g.D >> 1, Ho = g.H >> 1, Wo = g.W >> 1;
+    const int zo = sg.zz >> 1, yo = sg.yy >> 1, xo = xq >> 1;
+    if (gr.g_pool && zo < Do && yo < Ho && xo < Wo) {
+        const int64_t i = ((((int64_t)sg.b * Do + zo) * Ho + yo) * Wo + xo) * (CB_CO / 4) + c;
+        const uint32_t arg = __ldg(gr.pool_idx + i), k = (uint32_t)((sg.zz & 1) * 4 + (sg.yy & 1) * 2 + (xq & 1));
+        const float4 gp = __ldg(reinterpret_cast<const float4 *>(gr.g_pool) + i);
+        if ((arg & 0xffu) == k) v.x += gp.x;
+        if (((arg >> 8) & 0xffu) == k) v.y += gp.y;
+        if (((arg >> 16) & 0xffu) == k) v.z += gp.z;
+        if ((arg >> 24) == k) v.w += gp.w;
+    }
+    return v;
 }
 
 // sum the 2*CB_CO per-lane accumulators over the block, one row of `partial` per block
@@ -272,7 +302,8 @@ __global__ void cb_stats_finalize_kernel(const float *__restrict__ partial, int 
 __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                                  const float *__restrict__ bias, const float *__restrict__ mean,
                                                                  const float *__restrict__ invstd, const float *__restrict__ gamma,
-                                                                 const float *__restrict__ beta, const CbGeom g, float *__restrict__ y) {
+                                                                 const float *__restrict__ beta, const CbGeom g, float *__restrict__ y,
+                                                                 uint4 *__restrict__ y_bf16) {
     extern __shared__ __align__(16) uint8_t cb_dyn[];
     CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
     cb_load_weights(s, w, bias);
@@ -290,11 +321,20 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__
         for (int j = 0; j < 2; ++j)
             if (sg.x0 + lane + 32 * j < g.W) {
                 float4 *dst = reinterpret_cast<float4 *>(y + (sg.p0 + lane + 32 * j) * CB_CO);
+                float o[CB_CO];
 #pragma unroll
-                for (int c = 0; c < CB_CO / 4; ++c)
-                    dst[c] = make_float4(fmaf(a[j][4 * c], s.ch[0][4 * c], s.ch[1][4 * c]), fmaf(a[j][4 * c + 1], s.ch[0][4 * c + 1], s.ch[1][4 * c + 1]),
-                                         fmaf(a[j][4 * c + 2], s.ch[0][4 * c + 2], s.ch[1][4 * c + 2]),
-                                         fmaf(a[j][4 * c + 3], s.ch[0][4 * c + 3], s.ch[1][4 * c + 3]));
+                for (int c = 0; c < CB_CO; ++c) o[c] = fmaf(a[j][c], s.ch[0][c], s.ch[1][c]);
+#pragma unroll
+                for (int c = 0; c < CB_CO / 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                if (y_bf16) {   // the gather's bf16 NDHWC copy of the volume, saving a separate pack pass
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        __nv_bfloat162 q[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) q[e] = __floats2bfloat162_rn(o[8 * h + 2 * e], o[8 * h + 2 * e + 1]);
+                        y_bf16[(sg.p0 + lane + 32 * j) * 2 + h] = *reinterpret_cast<uint4 *>(q);
+                    }
+                }
             }
     });
 }
@@ -302,8 +342,8 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__
 // ---- backward pass 1: sum gy, sum gy * xhat ---------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_WARPS * 32) cb_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                                       const float *__restrict__ bias, const float *__restrict__ mean,
-                                                                      const float *__restrict__ invstd, const float *__restrict__ gy,
-                                                                      const CbGeom g, float *__restrict__ partial) {
+                                                                      const float *__restrict__ invstd, const CbGrad gr, const CbGeom g,
+                                                                      float *__restrict__ partial) {
     extern __shared__ __align__(16) uint8_t cb_dyn[];
     CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
     cb_load_weights(s, w, bias);
@@ -319,12 +359,9 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_bwd_reduce_kernel(const floa
     cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {
         float4 gq[2][CB_CO / 4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const bool ok = sg.x0 + lane + 32 * j < g.W;
-            const float4 *src = reinterpret_cast<const float4 *>(gy + (sg.p0 + lane + 32 * j) * CB_CO);
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int c = 0; c < CB_CO / 4; ++c) gq[j][c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (int c = 0; c < CB_CO / 4; ++c) gq[j][c] = cb_load_grad(gr, g, sg, sg.x0 + lane + 32 * j, c);
         float a[2][CB_CO];
         cb_conv_relu(s, tile, lane, a);
 #pragma unroll
@@ -367,7 +404,7 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
                                                                      const float *__restrict__ bias, const float *__restrict__ mean,
                                                                      const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                                      const float *__restrict__ gbeta, const float *__restrict__ ggamma,
-                                                                     const float *__restrict__ gy, const CbGeom g, float inv_n,
+                                                                     const CbGrad gr, const CbGeom g, float inv_n,
                                                                      float *__restrict__ partial /* [grid][28][16] */) {
     extern __shared__ __align__(16) uint8_t cb_dyn[];
     CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
@@ -404,12 +441,9 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
         const int x0 = sg.x0;
         float4 gv4[2][CB_CO / 4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const bool ok = x0 + lane + 32 * j < g.W;
-            const float4 *src = reinterpret_cast<const float4 *>(gy + (sg.p0 + lane + 32 * j) * CB_CO);
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int c = 0; c < CB_CO / 4; ++c) gv4[j][c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (int c = 0; c < CB_CO / 4; ++c) gv4[j][c] = cb_load_grad(gr, g, sg, x0 + lane + 32 * j, c);
         float a[2][CB_CO];
         cb_conv_relu(s, tile, lane, a);
 #pragma unroll
@@ -551,22 +585,24 @@ int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, i
 }
 
 int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, const float *mean, const float *invstd, const float *gamma,
-                            const float *beta, int B, int D, int H, int W, int Co, float *y, void *stream) {
+                            const float *beta, int B, int D, int H, int W, int Co, float *y, uint16_t *y_bf16, void *stream) {
     SVR_REQUIRE(x && w && mean && invstd && y, "conv1_relu_bn_apply: null pointer");
     SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
     CbGeom g;
     SVR_REQUIRE(cb_geom(g, B, D, H, W), "conv1_relu_bn_apply: grid too large");
     if (g.n_vox == 0) return 0;
     if (int rc = cb_attrs()) return rc;
-    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, CB_SMEM, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y);
+    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, CB_SMEM, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y, reinterpret_cast<uint4 *>(y_bf16));
     SVR_LAUNCH_CHECK();
     return 0;
 }
 
 int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, const float *mean, const float *invstd, const float *gamma,
-                          const float *gy, int B, int D, int H, int W, int Co, float *gw, float *gb, float *ggamma, float *gbeta,
-                          void *workspace, size_t workspace_bytes, void *stream) {
-    SVR_REQUIRE(x && w && mean && invstd && gy && gw && gb && ggamma && gbeta && workspace, "conv1_relu_bn_bwd: null pointer");
+                          const float *gy, const float *g_pooled, const uint32_t *pool_idx, int B, int D, int H, int W, int Co, float *gw,
+                          float *gb, float *ggamma, float *gbeta, void *workspace, size_t workspace_bytes, void *stream) {
+    SVR_REQUIRE(x && w && mean && invstd && gw && gb && ggamma && gbeta && workspace, "conv1_relu_bn_bwd: null pointer");
+    SVR_REQUIRE((g_pooled == nullptr) == (pool_idx == nullptr), "conv1_relu_bn_bwd: g_pooled and pool_idx go together");
+    const CbGrad gr{gy, g_pooled, pool_idx};
     SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
     SVR_REQUIRE(workspace_bytes >= svr_conv1_bn_workspace_bytes(), "conv1_relu_bn_bwd: workspace too small");
     CbGeom g;
@@ -575,9 +611,9 @@ int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, con
     float *p32 = (float *)workspace, *p448 = p32 + (size_t)sm_count() * 8 * 32;
     cudaStream_t st = as_stream(stream);
     if (int rc = cb_attrs()) return rc;
-    cb_bwd_reduce_kernel<<<grid, CB_WARPS * 32, CB_SMEM, st>>>(x, w, bias, mean, invstd, gy, g, p32);
+    cb_bwd_reduce_kernel<<<grid, CB_WARPS * 32, CB_SMEM, st>>>(x, w, bias, mean, invstd, gr, g, p32);
     cb_bwd_finalize_kernel<<<1, 1024, 0, st>>>(p32, grid, gbeta, ggamma);
-    cb_bwd_wgrad_kernel<<<grid, CB_WARPS * 32, CB_SMEM_WGRAD, st>>>(x, w, bias, mean, invstd, gamma, gbeta, ggamma, gy, g, (float)(1.0 / (double)g.n_vox), p448);
+    cb_bwd_wgrad_kernel<<<grid, CB_WARPS * 32, CB_SMEM_WGRAD, st>>>(x, w, bias, mean, invstd, gamma, gbeta, ggamma, gr, g, (float)(1.0 / (double)g.n_vox), p448);
     cb_wgrad_reduce_kernel<<<ceil_div(28 * CB_CO, 32), 256, 0, st>>>(p448, grid, gw, gb);
     SVR_LAUNCH_CHECK();
     return 0;

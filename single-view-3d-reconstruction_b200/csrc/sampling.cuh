@@ -296,16 +296,6 @@ __device__ __forceinline__ uint4 gather_unit_fast(const UnitCtx &c, int align, f
     uint4 raw[8];
     float w[8];
     const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
-#if defined(SVR_FQ_DBG) && SVR_FQ_DBG == 1
-    if (true) {   // experiment: no global loads
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t t = (uint32_t)(uintptr_t)ptr + k;
-            raw[k] = make_uint4(t, t * 3u, t * 5u, t * 7u);
-            w[k] = wxy[k & 3] * ((k & 4) ? wz1 : wz0);
-        }
-    } else
-#endif
     if (interior && !c.coarse) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -326,15 +316,6 @@ __device__ __forceinline__ uint4 gather_unit_fast(const UnitCtx &c, int align, f
             w[k] = in ? wxy[k & 3] * ((k & 4) ? wz1 : wz0) : 0.f;
         }
     }
-#if defined(SVR_FQ_DBG) && SVR_FQ_DBG == 2
-    {   // experiment: loads only, no blend
-        uint4 o = raw[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) { o.x ^= raw[k].x; o.y ^= raw[k].y; o.z ^= raw[k].z; o.w ^= raw[k].w; }
-        o.x ^= __float_as_uint(w[0] + w[7]);
-        return o;
-    }
-#endif
     unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {

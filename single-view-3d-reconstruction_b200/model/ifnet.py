@@ -103,7 +103,8 @@ class _ExtractorBase(nn.Module):
         return self.actvn(self._conv(conv, x))
 
     def _first_stage(self, conv, bn, x):
-        """bn(relu(conv(x))) of the 128-net's first stage.  Fused (csrc/conv_in_bn.cu: the 0.5 GB pre-BN activation
+        """(y, pooled) with y = bn(relu(conv(x))) of the 128-net's first stage and pooled = maxpool(y), or (y, None)
+        when the pooling is left to the caller.  Fused (csrc/conv_in_bn.cu: the 0.5 GB pre-BN activation
         is recomputed from the one-channel input instead of stored and re-read four times) when the pair is the
         reference's Conv3d(1,16,3,padding=1) + BatchNorm3d(16) in channels-last fp32 and no input gradient is
         needed; otherwise the two modules run one after the other."""
@@ -115,8 +116,10 @@ class _ExtractorBase(nn.Module):
             training = bn.training or not bn.track_running_stats
             wants_grad = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in (conv.weight, conv.bias, bn.weight, bn.bias))
             if training or not wants_grad:
-                return ops.conv1_relu_bn_channels_last(x, conv, bn)
-        return bn(self._first_conv_relu(conv, x))
+                if min(x.shape[2:]) >= 2:
+                    return ops.conv1_relu_bn_channels_last(x, conv, bn, with_pool=True)
+                return ops.conv1_relu_bn_channels_last(x, conv, bn), None
+        return bn(self._first_conv_relu(conv, x)), None
 
     def _prep(self, x):
         """Encoder input / weights in channels_last_3d when enabled (see ``args.channels_last``)."""
@@ -209,11 +212,11 @@ class IFNetFeatureExtractor128(_ExtractorBase):
         self.displacments = _displacements(self.displacement)
 
     def encode(self, x):
-        net = self._first_stage(self.conv_in, self.conv_in_bn, self._prep(x))
+        net, pooled = self._first_stage(self.conv_in, self.conv_in_bn, self._prep(x))
         vols = [net]
         for ca, cb, bn in ((self.conv_0, self.conv_0_1, self.conv0_1_bn), (self.conv_1, self.conv_1_1, self.conv1_1_bn),
                            (self.conv_2, self.conv_2_1, self.conv2_1_bn), (self.conv_3, self.conv_3_1, self.conv3_1_bn)):
-            net = self._pool(net)
+            net, pooled = (pooled if pooled is not None else self._pool(net)), None
             net = bn(self._conv_relu(cb, self._conv_relu(ca, net)))
             vols.append(net)
         return vols

@@ -218,10 +218,13 @@ def conv1_relu_channels_last(x, weight, bias):
 class _Conv1ReLUBN(torch.autograd.Function):
     """BatchNorm3d(relu(Conv3d(1 -> 16, 3, padding=1)(x))) without ever storing the pre-BN activation
     (csrc/conv_in_bn.cu): training mode = batch statistics (running statistics updated in place), eval mode =
-    running statistics (forward only)."""
+    running statistics (forward only).  With ``with_pool`` the following nn.MaxPool3d(2) is part of the stage:
+    outputs (y, pooled, y_bf16); y then has a single consumer (the query path), so autograd never sums the pooling
+    branch into its gradient -- the backward kernels route the pooled gradient through the winner codes on the fly.
+    y_bf16 is the gather's bf16 NDHWC copy of y (non-differentiable, see ``pack_volume``)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, update_running, momentum, eps):
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, update_running, momentum, eps, with_pool):
         x0 = _dev_f32(x, "x")
         B, _, D, H, W = x0.shape
         Co = weight.shape[0]
@@ -243,51 +246,75 @@ class _Conv1ReLUBN(torch.autograd.Function):
             mean = running_mean.detach().float().contiguous()
             invstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
         y = torch.empty((B, D, H, W, Co), device=dev, dtype=torch.float32)
+        y_bf16 = torch.empty((B, D, H, W, Co), device=dev, dtype=_BF16)
         _abi.check(_lib().svr_conv1_relu_bn_apply(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), _ptr(be),
-                                                  B, D, H, W, Co, y.data_ptr(), _stream()), "conv1_relu_bn_apply")
-        ctx.save_for_backward(x0, w, b, ga, mean, invstd)
+                                                  B, D, H, W, Co, y.data_ptr(), y_bf16.data_ptr(), _stream()), "conv1_relu_bn_apply")
+        pooled = idx = None
+        if with_pool:
+            pooled = torch.empty((B, D // 2, H // 2, W // 2, Co), device=dev, dtype=torch.float32)
+            idx = torch.empty((pooled.numel() // 4,), device=dev, dtype=torch.int32)
+            _abi.check(_lib().svr_maxpool2_cl_fwd(y.data_ptr(), B, D, H, W, Co, pooled.data_ptr(), idx.data_ptr(), _stream()), "maxpool_fwd")
+        ctx.save_for_backward(x0, w, b, ga, mean, invstd, idx)
         ctx.training = bool(training)
         ctx.wshape = weight.shape
         ctx.has = (bias is not None, gamma is not None, beta is not None)
-        return y.permute(0, 4, 1, 2, 3)
+        ctx.mark_non_differentiable(y_bf16)
+        yv = y.permute(0, 4, 1, 2, 3)
+        if with_pool:
+            return yv, pooled.permute(0, 4, 1, 2, 3), y_bf16
+        return yv, y_bf16
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, *rest):
         if not ctx.training:
             raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage has no eval-mode backward; use the unfused modules")
         if ctx.needs_input_grad[0]:
             raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage does not produce an input gradient")
-        x0, w, b, ga, mean, invstd = ctx.saved_tensors
+        x0, w, b, ga, mean, invstd, idx = ctx.saved_tensors
+        gpool = rest[0] if idx is not None else None
         B, _, D, H, W = x0.shape
         Co = w.shape[0]
         dev = x0.device
-        g = gy.permute(0, 2, 3, 4, 1)
-        if not g.is_contiguous():
-            g = g.contiguous()
-        g = _dev_f32(g, "grad")
+
+        def ndhwc(t):
+            if t is None:
+                return None
+            t = t.permute(0, 2, 3, 4, 1)
+            return _dev_f32(t, "grad")       # contiguous NDHWC (a no-op for channels-last gradients)
+
+        g, gp = ndhwc(gy), ndhwc(gpool)
         gw = torch.empty((Co, 27), device=dev, dtype=torch.float32)
         gb, gga, gbe = (torch.empty((Co,), device=dev, dtype=torch.float32) for _ in range(3))
         nbytes = _lib().svr_conv1_bn_workspace_bytes()
         ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
-        _abi.check(_lib().svr_conv1_relu_bn_bwd(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), g.data_ptr(),
-                                                B, D, H, W, Co, gw.data_ptr(), gb.data_ptr(), gga.data_ptr(), gbe.data_ptr(), ws.data_ptr(),
-                                                nbytes, _stream()), "conv1_relu_bn_bwd")
+        _abi.check(_lib().svr_conv1_relu_bn_bwd(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), _ptr(g),
+                                                _ptr(gp), _ptr(idx) if gp is not None else None, B, D, H, W, Co, gw.data_ptr(), gb.data_ptr(),
+                                                gga.data_ptr(), gbe.data_ptr(), ws.data_ptr(), nbytes, _stream()), "conv1_relu_bn_bwd")
         has_b, has_g, has_be = ctx.has
         return (None, gw.view(ctx.wshape), gb if has_b else None, gga if has_g else None, gbe if has_be else None, None, None, None, None, None,
-                None)
+                None, None)
 
 
-def conv1_relu_bn_channels_last(x, conv, bn):
+# bf16 NDHWC copy of a volume produced by the stage that wrote the fp32 one (weak reference to the fp32 tensor OBJECT ->
+# packed copy): pack_volume() returns it instead of re-reading the fp32 volume.
+_PREPACKED = {"src": None, "packed": None}
+
+
+def conv1_relu_bn_channels_last(x, conv, bn, with_pool=False):
     """bn(relu(conv(x))) for the (Conv3d(1,16,3,padding=1), BatchNorm3d(16)) pair; mirrors nn.BatchNorm3d's side
-    effects (running statistics and num_batches_tracked in training mode)."""
+    effects (running statistics and num_batches_tracked in training mode).  Returns y, or (y, maxpool2(y))."""
+    import weakref
     track = bn.track_running_stats and bn.running_mean is not None
     update = bn.training and track
     if update and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     use_batch = bn.training or not track
     rm, rv = (bn.running_mean, bn.running_var) if track else (None, None)
-    return _Conv1ReLUBN.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, use_batch, update,
-                              bn.momentum if bn.momentum is not None else 0.0, bn.eps)
+    out = _Conv1ReLUBN.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, use_batch, update,
+                             bn.momentum if bn.momentum is not None else 0.0, bn.eps, bool(with_pool))
+    y, packed = out[0], out[-1]
+    _PREPACKED["src"], _PREPACKED["packed"] = weakref.ref(y), packed
+    return (y, out[1]) if with_pool else y
 
 
 class _ConvBf16Backward(torch.autograd.Function):
@@ -400,6 +427,9 @@ def pack_volume(v: torch.Tensor) -> torch.Tensor:
     """fp32 (B,C,D,H,W), any strides -> bf16 NDHWC contiguous (B,D,H,W,C)."""
     if not v.is_cuda:
         raise RuntimeError("svr_b200: feature volumes must be CUDA tensors; there is no CPU path")
+    src = _PREPACKED["src"]
+    if src is not None and src() is v:            # the producing stage already wrote the bf16 copy
+        return _PREPACKED["packed"]
     if v.dtype != torch.float32:
         v = v.float()
     B, Cc, D, H, W = v.shape

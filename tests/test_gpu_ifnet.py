@@ -344,10 +344,16 @@ def test_first_stage_fused_conv_relu_bn(shape):
             bn.bias.copy_(torch.randn(16, generator=g) * 0.1)
         conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
         cot = torch.randn((B, 16, D, H, W), generator=g).cuda()
-        y = ops.conv1_relu_bn_channels_last(x, conv, bn)
-        (y * cot).sum().backward()
+        cot_p = torch.randn((B, 16, D // 2, H // 2, W // 2), generator=g).cuda()
+        # fused stage incl. the following MaxPool3d(2): y feeds the query path, pooled the next convolution
+        y, yp = ops.conv1_relu_bn_channels_last(x, conv, bn, with_pool=True)
+        packed = ops.pack_volume(y)
+        ((y * cot).sum() + (yp * cot_p).sum()).backward()
         yr = bn_r(torch.relu(conv_r(x)))
-        (yr * cot).sum().backward()
+        ypr = torch.nn.functional.max_pool3d(yr, 2)
+        ((yr * cot).sum() + (ypr * cot_p).sum()).backward()
+        assert torch.equal(yp, torch.nn.functional.max_pool3d(y, 2))
+        assert torch.equal(packed, y.permute(0, 2, 3, 4, 1).contiguous().bfloat16())     # bf16 copy written by the stage
 
         def rel(a, b):
             return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
