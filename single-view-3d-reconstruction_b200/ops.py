@@ -259,6 +259,7 @@ class _Conv1ReLUBN(torch.autograd.Function):
         ctx.wshape = weight.shape
         ctx.has = (bias is not None, gamma is not None, beta is not None)
         ctx.mark_non_differentiable(y_bf16)
+        ctx.set_materialize_grads(False)     # no zero-filled stand-ins for the gradients of unused / non-differentiable outputs
         yv = y.permute(0, 4, 1, 2, 3)
         if with_pool:
             return yv, pooled.permute(0, 4, 1, 2, 3), y_bf16
@@ -327,7 +328,7 @@ class _ConvBf16Backward(torch.autograd.Function):
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
         y = torch.nn.functional.conv3d(x, weight, bias, stride, padding, dilation, groups)
         cl = torch.channels_last_3d
-        ctx.save_for_backward(x.detach().to(torch.bfloat16).contiguous(memory_format=cl), weight)
+        ctx.save_for_backward(_to_bf16_channels_last(x.detach()), weight)
         ctx.conf = (stride, padding, dilation, groups, bias is not None)
         return y
 
@@ -359,7 +360,7 @@ class _ConvBiasReLU(torch.autograd.Function):
         rows = y.numel() // Co
         _abi.check(_lib().svr_bias_relu_cl(y.data_ptr(), _ptr(bias.detach() if bias is not None else None), rows, Co, _stream()), "bias_relu_cl")
         xs = x.detach()
-        ctx.save_for_backward(xs.to(torch.bfloat16).contiguous(memory_format=cl) if bf16_backward else xs, weight, y)
+        ctx.save_for_backward(_to_bf16_channels_last(xs) if bf16_backward else xs, weight, y)
         ctx.conf = (stride, padding, dilation, groups, bias is not None, bool(bf16_backward))
         return y
 
@@ -395,6 +396,14 @@ class _ConvBiasReLU(torch.autograd.Function):
 
 def conv3d_bias_relu(x, conv, bf16_backward):
     return _ConvBiasReLU.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, bf16_backward)
+
+
+def _to_bf16_channels_last(x):
+    """bf16 copy of a channels-last fp32 activation through the vectorised convert kernel (torch's .to() falls back to
+    a strided element-wise copy on permuted views: 2 TB/s)."""
+    if x.dtype == torch.float32 and x.is_cuda and x.dim() == 5 and x.is_contiguous(memory_format=torch.channels_last_3d):
+        return pack_volume(x).permute(0, 4, 1, 2, 3)
+    return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
 
 
 def conv3d_bf16_backward(x, conv):
