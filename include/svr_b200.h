@@ -212,11 +212,14 @@ int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, cons
  *   stats : training-mode batch mean / 1/sqrt(var+eps) (biased variance) into mean[16], invstd[16]; running_mean /
  *           running_var (nullable) get torch's momentum update (unbiased variance).
  *   apply : y (B,D,H,W,16) from given mean / invstd (batch statistics, or running statistics in eval mode); y_bf16
- *           (nullable) receives the bf16 copy the gather kernels sample (what svr_pack_volume would produce).
+ *           (nullable) receives the bf16 copy the gather kernels sample (what svr_pack_volume would produce),
+ *           relu_mask (nullable, one uint16 per voxel) the bits [relu(conv)_c > 0].
  *   bwd   : gw (16,27), gb (16), ggamma (16), gbeta (16), training-mode BN backward.  The gradient of y is
  *           gy (B,D,H,W,16, nullable) plus, when the stage's nn.MaxPool3d(2) (ifnet.py:169) is fused, the gradient
  *           g_pooled (B,D/2,H/2,W/2,16) of the pooled tensor routed through pool_idx (winner codes written by
  *           svr_maxpool2_cl_fwd; both nullable): neither the pooling backward nor the sum is materialised.
+ *           With y and relu_mask (both nullable, as written by apply; beta then required when BN has one) the
+ *           normalised activation is read back instead of recomputed.
  * x (B,D,H,W) fp32, w (16,27), bias / gamma / beta nullable.  Workspace: svr_conv1_bn_workspace_bytes().       */
 size_t svr_conv1_bn_workspace_bytes(void);
 int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, int B, int D, int H, int W, int Co, float eps,
@@ -224,11 +227,11 @@ int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, i
                             size_t workspace_bytes, void *stream);
 int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, const float *mean, const float *invstd,
                             const float *gamma, const float *beta, int B, int D, int H, int W, int Co, float *y, uint16_t *y_bf16,
-                            void *stream);
+                            uint16_t *relu_mask, void *stream);
 int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, const float *mean, const float *invstd,
-                          const float *gamma, const float *gy, const float *g_pooled, const uint32_t *pool_idx, int B, int D,
-                          int H, int W, int Co, float *gw, float *gb, float *ggamma, float *gbeta, void *workspace,
-                          size_t workspace_bytes, void *stream);
+                          const float *gamma, const float *beta, const float *y, const uint16_t *relu_mask, const float *gy,
+                          const float *g_pooled, const uint32_t *pool_idx, int B, int D, int H, int W, int Co, float *gw,
+                          float *gb, float *ggamma, float *gbeta, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Elementwise glue of the encoder's Conv3d -> ReLU layers (ifnet.py:127-135,165-183 `self.actvn(self.conv_x(net))`),
  * channels-last fp32 activations viewed as (rows = B*D*H*W, C), C % 4 == 0 and 256 % (C/4) == 0.

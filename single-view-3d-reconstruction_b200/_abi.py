@@ -77,8 +77,8 @@ _SIGS = {
     "svr_conv1_bn_workspace_bytes": (C.c_size_t, []),
     "svr_conv1_relu_bn_stats": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp,
                                           C.c_size_t, vp]),
-    "svr_conv1_relu_bn_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
-    "svr_conv1_relu_bn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
+    "svr_conv1_relu_bn_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "svr_conv1_relu_bn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                         C.c_size_t, vp]),
     "svr_bias_relu_cl": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
     "svr_relu_bwd_cl_workspace_bytes": (C.c_size_t, [C.c_int]),

@@ -12,7 +12,10 @@
 //   bwd 1   : a recomputed, sum gy and sum gy * xhat                    (reads x, gy)
 //   bwd 2   : a recomputed, da -> ReLU mask -> weight/bias gradient     (reads x, gy)
 // `a` is recomputed by the same inlined routine everywhere, so the ReLU mask of the backward pass is
-// bit-identical to the forward activation.
+// bit-identical to the forward activation.  When the caller keeps y and the ReLU bit mask the apply pass can
+// emit (16 bits per voxel), the backward passes take xhat = (y - beta) / gamma and the mask from memory instead
+// (0.56 GB more traffic, 0.2 ms less arithmetic per pass at batch 4 x 128^3); they fall back to the recomputation
+// if any |gamma| is too small to invert.
 //
 // Work unit: a warp owns a 64-voxel segment of an x-row; the 3x3 neighbouring rows (with halo) are staged in
 // a warp-private shared tile, lane v computes the 16 channels of voxels v and v+32 (f32x2 FMAs, one broadcast
@@ -59,7 +62,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 struct CbShared {
     ulonglong2 wt[27][CB_CO / 4];         // [tap][channel quad] as two f32x2 pairs
     float4 bs[CB_CO / 4];
-    float ch[4][CB_CO];                   // per-channel constants of the pass
+    float ch[6][CB_CO];                   // per-channel constants of the pass
     float tile[CB_WARPS][2][CB_TILE];     // double-buffered: the next segment's rows arrive by cp.async during the math
 };
 
@@ -94,17 +97,22 @@ struct CbSeg {
 // Issues the asynchronous copies of the 3x3 rows x0-1 .. x0+64 of x into `tile` (tile[r][e] = x at x0 - 1 + e, zero
 // outside the volume) and commits them as one cp.async group.  The caller must have passed a __syncwarp since the
 // last reader of `tile`.
-__device__ __forceinline__ CbSeg cb_issue(const CbGeom &g, const float *__restrict__ x, int seg, int lane, float *tile) {
+__device__ __forceinline__ CbSeg cb_decode(const CbGeom &g, int seg) {
     const int row = seg / g.segs_per_row;
     CbSeg sg;
     sg.x0 = (seg - row * g.segs_per_row) * CB_SEG;
-    const int yy = row % g.H, r2 = row / g.H;
-    const int zz = r2 % g.D, b = r2 / g.D;
-    const int64_t base = (((int64_t)b * g.D + zz) * g.H + yy) * g.W;
-    sg.p0 = base + sg.x0;
-    sg.yy = yy;
-    sg.zz = zz;
-    sg.b = b;
+    sg.yy = row % g.H;
+    const int r2 = row / g.H;
+    sg.zz = r2 % g.D;
+    sg.b = r2 / g.D;
+    sg.p0 = (((int64_t)sg.b * g.D + sg.zz) * g.H + sg.yy) * g.W + sg.x0;
+    return sg;
+}
+
+__device__ __forceinline__ CbSeg cb_issue(const CbGeom &g, const float *__restrict__ x, int seg, int lane, float *tile) {
+    const CbSeg sg = cb_decode(g, seg);
+    const int yy = sg.yy, zz = sg.zz;
+    const int64_t base = sg.p0 - sg.x0;
     const int xa = sg.x0 - 1 + lane;
     const uint32_t sz_a = (xa >= 0 && xa < g.W) ? 4u : 0u, sz_b = (xa + 32 < g.W) ? 4u : 0u, sz_c = (xa + 64 < g.W) ? 4u : 0u;
     const float *src0 = x + base + xa;
@@ -195,7 +203,19 @@ struct CbGrad {
     const float *gy;
     const float *g_pool;
     const uint32_t *pool_idx;
+    const float *y;          // stage output (nullable): with relu_mask, replaces the recomputation of the activation
+    const uint16_t *relu_mask;
+    const float *gamma, *beta;
 };
+
+// true when xhat can be taken from y: y and the mask are given and every gamma is safely invertible
+// (s.ch[4] = 1/gamma, s.ch[5] = beta must be loaded; uniform over the grid)
+__device__ __forceinline__ bool cb_from_y(const CbGrad &gr) {
+    if (!gr.y || !gr.relu_mask) return false;
+    bool ok = true;
+    for (int c = 0; c < CB_CO; ++c) ok = ok && fabsf(gr.gamma ? gr.gamma[c] : 1.f) >= 1e-6f;
+    return ok;
+}
 __device__ __forceinline__ float4 cb_load_grad(const CbGrad &gr, const CbGeom &g, const CbSeg &sg, int xq, int c) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (xq >= g.W) return v;
@@ -212,6 +232,40 @@ __device__ __forceinline__ float4 cb_load_grad(const CbGrad &gr, const CbGeom &g
         if ((arg >> 24) == k) v.w += gp.w;
     }
     return v;
+}
+
+// (voxel, quad) item of the from-y passes: all global loads of a batch are issued before any is consumed (a warp keeps
+// 4 x 4 independent 16-byte loads in flight; one load-use round trip per item made the passes latency bound).
+struct CbItem {
+    float4 gy, y, gp;
+    uint32_t arg, mask;
+    bool ok, pooled;
+    uint32_t k;
+};
+__device__ __forceinline__ void cb_item_load(const CbGrad &gr, const CbGeom &g, const CbSeg &sg, int v, int q, CbItem &it) {
+    const int xq = sg.x0 + v;
+    it.ok = xq < g.W;
+    const int64_t vox = sg.p0 + v;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    it.gy = (it.ok && gr.gy) ? __ldg(reinterpret_cast<const float4 *>(gr.gy + vox * CB_CO) + q) : z4;
+    it.y = it.ok ? __ldg(reinterpret_cast<const float4 *>(gr.y + vox * CB_CO) + q) : z4;
+    it.mask = it.ok ? (uint32_t)__ldg(gr.relu_mask + vox) >> (4 * q) : 0u;
+    const int Do = g.D >> 1, Ho = g.H >> 1, Wo = g.W >> 1;
+    const int zo = sg.zz >> 1, yo = sg.yy >> 1, xo = xq >> 1;
+    it.pooled = it.ok && gr.g_pool && zo < Do && yo < Ho && xo < Wo;
+    const int64_t i = ((((int64_t)sg.b * Do + zo) * Ho + yo) * Wo + xo) * (CB_CO / 4) + q;
+    it.arg = it.pooled ? __ldg(gr.pool_idx + i) : 0u;
+    it.gp = it.pooled ? __ldg(reinterpret_cast<const float4 *>(gr.g_pool) + i) : z4;
+    it.k = (uint32_t)((sg.zz & 1) * 4 + (sg.yy & 1) * 2 + (xq & 1));
+}
+__device__ __forceinline__ void cb_item_grad(const CbItem &it, float (&gv)[4]) {
+    gv[0] = it.gy.x; gv[1] = it.gy.y; gv[2] = it.gy.z; gv[3] = it.gy.w;
+    if (it.pooled) {
+        if ((it.arg & 0xffu) == it.k) gv[0] += it.gp.x;
+        if (((it.arg >> 8) & 0xffu) == it.k) gv[1] += it.gp.y;
+        if (((it.arg >> 16) & 0xffu) == it.k) gv[2] += it.gp.z;
+        if ((it.arg >> 24) == it.k) gv[3] += it.gp.w;
+    }
 }
 
 // sum the 2*CB_CO per-lane accumulators over the block, one row of `partial` per block
@@ -303,7 +357,7 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__
                                                                  const float *__restrict__ bias, const float *__restrict__ mean,
                                                                  const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                                  const float *__restrict__ beta, const CbGeom g, float *__restrict__ y,
-                                                                 uint4 *__restrict__ y_bf16) {
+                                                                 uint4 *__restrict__ y_bf16, uint16_t *__restrict__ relu_mask) {
     extern __shared__ __align__(16) uint8_t cb_dyn[];
     CbShared &s = *reinterpret_cast<CbShared *>(cb_dyn);
     cb_load_weights(s, w, bias);
@@ -326,6 +380,12 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_apply_kernel(const float *__
                 for (int c = 0; c < CB_CO; ++c) o[c] = fmaf(a[j][c], s.ch[0][c], s.ch[1][c]);
 #pragma unroll
                 for (int c = 0; c < CB_CO / 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                if (relu_mask) {
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int c = 0; c < CB_CO; ++c) m |= (a[j][c] > 0.f ? 1u : 0u) << c;
+                    relu_mask[sg.p0 + lane + 32 * j] = (uint16_t)m;
+                }
                 if (y_bf16) {   // the gather's bf16 NDHWC copy of the volume, saving a separate pack pass
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -350,12 +410,70 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cb_bwd_reduce_kernel(const floa
     if (threadIdx.x < CB_CO) {
         s.ch[0][threadIdx.x] = mean[threadIdx.x];
         s.ch[1][threadIdx.x] = invstd[threadIdx.x];
+        s.ch[4][threadIdx.x] = 1.f / (gr.gamma ? gr.gamma[threadIdx.x] : 1.f);
+        s.ch[5][threadIdx.x] = gr.beta ? gr.beta[threadIdx.x] : 0.f;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     float s1[CB_CO], s2[CB_CO];
 #pragma unroll
     for (int c = 0; c < CB_CO; ++c) s1[c] = s2[c] = 0.f;
+    if (cb_from_y(gr)) {
+        // pure stream of gy (+ pooled branch) and y, no stencil.  Lane = (voxel, channel quad): consecutive lanes read
+        // consecutive 16-byte pieces, every load instruction is one fully used 512-byte run.
+        const int warp = threadIdx.x >> 5, q = lane & 3;
+        float bq[4], iq[4], t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            bq[e] = s.ch[5][4 * q + e];
+            iq[e] = s.ch[4][4 * q + e];
+        }
+        for (int seg = blockIdx.x * CB_WARPS + warp; seg < g.n_segs; seg += gridDim.x * CB_WARPS) {
+            const CbSeg sg = cb_decode(g, seg);
+#pragma unroll
+            for (int i0 = 0; i0 < CB_SEG / 8; i0 += 4) {
+                CbItem it[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cb_item_load(gr, g, sg, (i0 + i) * 8 + (lane >> 2), q, it[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float gv[4];
+                    cb_item_grad(it[i], gv);
+                    const float yy4[4] = {it[i].y.x, it[i].y.y, it[i].y.z, it[i].y.w};
+                    if (it[i].ok) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            t1[e] += gv[e];
+                            t2[e] = fmaf(gv[e], (yy4[e] - bq[e]) * iq[e], t2[e]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int o = 16; o >= 4; o >>= 1) {
+                t1[e] += __shfl_xor_sync(0xffffffffu, t1[e], o);
+                t2[e] += __shfl_xor_sync(0xffffffffu, t2[e], o);
+            }
+        float *red = &s.tile[0][0][0];
+        __syncthreads();
+        if (lane < 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                red[warp * 32 + 4 * lane + e] = t1[e];
+                red[warp * 32 + CB_CO + 4 * lane + e] = t2[e];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float vsum = 0.f;
+            for (int ww = 0; ww < CB_WARPS; ++ww) vsum += red[ww * 32 + threadIdx.x];
+            partial[(int64_t)blockIdx.x * 32 + threadIdx.x] = vsum;
+        }
+        return;
+    }
     cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {
         float4 gq[2][CB_CO / 4];
 #pragma unroll
@@ -416,9 +534,23 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
         s.ch[1][threadIdx.x] = invstd[threadIdx.x];
         s.ch[2][threadIdx.x] = (gamma ? gamma[threadIdx.x] : 1.f) * invstd[threadIdx.x];
         s.ch[3][threadIdx.x] = ggamma[threadIdx.x] * inv_n;
+        s.ch[4][threadIdx.x] = 1.f / (gr.gamma ? gr.gamma[threadIdx.x] : 1.f);
+        s.ch[5][threadIdx.x] = gr.beta ? gr.beta[threadIdx.x] : 0.f;
         k1[threadIdx.x] = gbeta[threadIdx.x] * inv_n;
     }
     __syncthreads();
+    const bool from_y = cb_from_y(gr);
+    // per-lane constants of the lane's channel quad (from-y path): gamma*invstd, mean(gy), mean(gy*xhat), 1/gamma, beta
+    const int q = threadIdx.x & 3;
+    float cq[5][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        cq[0][e] = s.ch[2][4 * q + e];
+        cq[1][e] = k1[4 * q + e];
+        cq[2][e] = s.ch[3][4 * q + e];
+        cq[3][e] = s.ch[4][4 * q + e];
+        cq[4][e] = s.ch[5][4 * q + e];
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *dz = park + warp * (CB_SEG * CB_DS);
     // MMA roles (m16n8k8: M = channel, N = tap, K = voxel): gq = lane / 4, t = lane % 4.
@@ -439,28 +571,52 @@ __global__ void __launch_bounds__(CB_WARPS * 32, 2) cb_bwd_wgrad_kernel(const fl
         for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
     cb_for_each_segment(g, x, s, [&](const float *tile, const CbSeg &sg) {   // __syncwarp after each body: parked rows consumed
         const int x0 = sg.x0;
-        float4 gv4[2][CB_CO / 4];
+        if (from_y) {
+            // lane = (voxel, channel quad): coalesced reads of gy, y and the mask; the masked gradient goes straight to its
+            // parked row
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+            for (int i0 = 0; i0 < CB_SEG / 8; i0 += 4) {
+                CbItem it[4];
 #pragma unroll
-            for (int c = 0; c < CB_CO / 4; ++c) gv4[j][c] = cb_load_grad(gr, g, sg, x0 + lane + 32 * j, c);
-        float a[2][CB_CO];
-        cb_conv_relu(s, tile, lane, a);
+                for (int i = 0; i < 4; ++i) cb_item_load(gr, g, sg, (i0 + i) * 8 + (lane >> 2), q, it[i]);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const bool ok = x0 + lane + 32 * j < g.W;
+                for (int i = 0; i < 4; ++i) {
+                    float gv[4], r[4];
+                    cb_item_grad(it[i], gv);
+                    const float yy4[4] = {it[i].y.x, it[i].y.y, it[i].y.z, it[i].y.w};
 #pragma unroll
-            for (int c = 0; c < CB_CO / 4; ++c) {
-                const float gv[4] = {gv4[j][c].x, gv4[j][c].y, gv4[j][c].z, gv4[j][c].w};
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int ch = 4 * c + e;
-                    const float xh = (a[j][ch] - s.ch[0][ch]) * s.ch[1][ch];
-                    const float da = s.ch[2][ch] * (gv[e] - k1[ch] - xh * s.ch[3][ch]);
-                    o[e] = (ok && a[j][ch] > 0.f) ? da : 0.f;
+                    for (int e = 0; e < 4; ++e) {
+                        const float xhat = (yy4[e] - cq[4][e]) * cq[3][e];
+                        const float da = cq[0][e] * (gv[e] - cq[1][e] - xhat * cq[2][e]);
+                        r[e] = ((it[i].mask >> e) & 1u) ? da : 0.f;      // mask is 0 outside the volume
+                    }
+                    *reinterpret_cast<float4 *>(dz + ((i0 + i) * 8 + (lane >> 2)) * CB_DS + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
                 }
-                *reinterpret_cast<float4 *>(dz + (lane + 32 * j) * CB_DS + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        } else {
+            float4 gv4[2][CB_CO / 4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int c = 0; c < CB_CO / 4; ++c) gv4[j][c] = cb_load_grad(gr, g, sg, x0 + lane + 32 * j, c);
+            float a[2][CB_CO];
+            cb_conv_relu(s, tile, lane, a);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool ok = x0 + lane + 32 * j < g.W;
+#pragma unroll
+                for (int c = 0; c < CB_CO / 4; ++c) {
+                    const float gv[4] = {gv4[j][c].x, gv4[j][c].y, gv4[j][c].z, gv4[j][c].w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ch = 4 * c + e;
+                        const float xhat = (a[j][ch] - s.ch[0][ch]) * s.ch[1][ch];
+                        const float da = s.ch[2][ch] * (gv[e] - k1[ch] - xhat * s.ch[3][ch]);
+                        o[e] = (ok && a[j][ch] > 0.f) ? da : 0.f;
+                    }
+                    *reinterpret_cast<float4 *>(dz + (lane + 32 * j) * CB_DS + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
+                }
             }
         }
         __syncwarp();
@@ -585,24 +741,27 @@ int svr_conv1_relu_bn_stats(const float *x, const float *w, const float *bias, i
 }
 
 int svr_conv1_relu_bn_apply(const float *x, const float *w, const float *bias, const float *mean, const float *invstd, const float *gamma,
-                            const float *beta, int B, int D, int H, int W, int Co, float *y, uint16_t *y_bf16, void *stream) {
+                            const float *beta, int B, int D, int H, int W, int Co, float *y, uint16_t *y_bf16, uint16_t *relu_mask,
+                            void *stream) {
     SVR_REQUIRE(x && w && mean && invstd && y, "conv1_relu_bn_apply: null pointer");
     SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
     CbGeom g;
     SVR_REQUIRE(cb_geom(g, B, D, H, W), "conv1_relu_bn_apply: grid too large");
     if (g.n_vox == 0) return 0;
     if (int rc = cb_attrs()) return rc;
-    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, CB_SMEM, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y, reinterpret_cast<uint4 *>(y_bf16));
+    cb_apply_kernel<<<cb_grid(g), CB_WARPS * 32, CB_SMEM, as_stream(stream)>>>(x, w, bias, mean, invstd, gamma, beta, g, y, reinterpret_cast<uint4 *>(y_bf16), relu_mask);
     SVR_LAUNCH_CHECK();
     return 0;
 }
 
 int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, const float *mean, const float *invstd, const float *gamma,
-                          const float *gy, const float *g_pooled, const uint32_t *pool_idx, int B, int D, int H, int W, int Co, float *gw,
-                          float *gb, float *ggamma, float *gbeta, void *workspace, size_t workspace_bytes, void *stream) {
+                          const float *beta, const float *y, const uint16_t *relu_mask, const float *gy, const float *g_pooled,
+                          const uint32_t *pool_idx, int B, int D, int H, int W, int Co, float *gw, float *gb, float *ggamma, float *gbeta,
+                          void *workspace, size_t workspace_bytes, void *stream) {
     SVR_REQUIRE(x && w && mean && invstd && gw && gb && ggamma && gbeta && workspace, "conv1_relu_bn_bwd: null pointer");
     SVR_REQUIRE((g_pooled == nullptr) == (pool_idx == nullptr), "conv1_relu_bn_bwd: g_pooled and pool_idx go together");
-    const CbGrad gr{gy, g_pooled, pool_idx};
+    SVR_REQUIRE((y == nullptr) == (relu_mask == nullptr), "conv1_relu_bn_bwd: y and relu_mask go together");
+    const CbGrad gr{gy, g_pooled, pool_idx, y, relu_mask, gamma, beta};
     SVR_REQUIRE(Co == CB_CO, "conv1_relu_bn: 16 output channels supported (got %d)", Co);
     SVR_REQUIRE(workspace_bytes >= svr_conv1_bn_workspace_bytes(), "conv1_relu_bn_bwd: workspace too small");
     CbGeom g;

@@ -224,7 +224,8 @@ class _Conv1ReLUBN(torch.autograd.Function):
     y_bf16 is the gather's bf16 NDHWC copy of y (non-differentiable, see ``pack_volume``)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, update_running, momentum, eps, with_pool):
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, update_running, momentum, eps, with_pool,
+                keep_for_backward):
         x0 = _dev_f32(x, "x")
         B, _, D, H, W = x0.shape
         Co = weight.shape[0]
@@ -247,14 +248,16 @@ class _Conv1ReLUBN(torch.autograd.Function):
             invstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
         y = torch.empty((B, D, H, W, Co), device=dev, dtype=torch.float32)
         y_bf16 = torch.empty((B, D, H, W, Co), device=dev, dtype=_BF16)
+        keep = bool(training) and bool(keep_for_backward)        # backward reads y and the ReLU bits instead of recomputing them
+        mask = torch.empty((B, D, H, W), device=dev, dtype=torch.int16) if keep else None
         _abi.check(_lib().svr_conv1_relu_bn_apply(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), _ptr(be),
-                                                  B, D, H, W, Co, y.data_ptr(), y_bf16.data_ptr(), _stream()), "conv1_relu_bn_apply")
+                                                  B, D, H, W, Co, y.data_ptr(), y_bf16.data_ptr(), _ptr(mask), _stream()), "conv1_relu_bn_apply")
         pooled = idx = None
         if with_pool:
             pooled = torch.empty((B, D // 2, H // 2, W // 2, Co), device=dev, dtype=torch.float32)
             idx = torch.empty((pooled.numel() // 4,), device=dev, dtype=torch.int32)
             _abi.check(_lib().svr_maxpool2_cl_fwd(y.data_ptr(), B, D, H, W, Co, pooled.data_ptr(), idx.data_ptr(), _stream()), "maxpool_fwd")
-        ctx.save_for_backward(x0, w, b, ga, mean, invstd, idx)
+        ctx.save_for_backward(x0, w, b, ga, be, mean, invstd, idx, y if keep else None, mask)
         ctx.training = bool(training)
         ctx.wshape = weight.shape
         ctx.has = (bias is not None, gamma is not None, beta is not None)
@@ -271,7 +274,7 @@ class _Conv1ReLUBN(torch.autograd.Function):
             raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage has no eval-mode backward; use the unfused modules")
         if ctx.needs_input_grad[0]:
             raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage does not produce an input gradient")
-        x0, w, b, ga, mean, invstd, idx = ctx.saved_tensors
+        x0, w, b, ga, be, mean, invstd, idx, y, mask = ctx.saved_tensors
         gpool = rest[0] if idx is not None else None
         B, _, D, H, W = x0.shape
         Co = w.shape[0]
@@ -288,12 +291,12 @@ class _Conv1ReLUBN(torch.autograd.Function):
         gb, gga, gbe = (torch.empty((Co,), device=dev, dtype=torch.float32) for _ in range(3))
         nbytes = _lib().svr_conv1_bn_workspace_bytes()
         ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
-        _abi.check(_lib().svr_conv1_relu_bn_bwd(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), _ptr(g),
-                                                _ptr(gp), _ptr(idx) if gp is not None else None, B, D, H, W, Co, gw.data_ptr(), gb.data_ptr(),
+        _abi.check(_lib().svr_conv1_relu_bn_bwd(x0.data_ptr(), w.data_ptr(), _ptr(b), mean.data_ptr(), invstd.data_ptr(), _ptr(ga), _ptr(be),
+                                                _ptr(y), _ptr(mask), _ptr(g), _ptr(gp), _ptr(idx) if gp is not None else None, B, D, H, W, Co, gw.data_ptr(), gb.data_ptr(),
                                                 gga.data_ptr(), gbe.data_ptr(), ws.data_ptr(), nbytes, _stream()), "conv1_relu_bn_bwd")
         has_b, has_g, has_be = ctx.has
         return (None, gw.view(ctx.wshape), gb if has_b else None, gga if has_g else None, gbe if has_be else None, None, None, None, None, None,
-                None, None)
+                None, None, None)
 
 
 # bf16 NDHWC copy of a volume produced by the stage that wrote the fp32 one (weak reference to the fp32 tensor OBJECT ->
@@ -312,7 +315,7 @@ def conv1_relu_bn_channels_last(x, conv, bn, with_pool=False):
     use_batch = bn.training or not track
     rm, rv = (bn.running_mean, bn.running_var) if track else (None, None)
     out = _Conv1ReLUBN.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, use_batch, update,
-                             bn.momentum if bn.momentum is not None else 0.0, bn.eps, bool(with_pool))
+                             bn.momentum if bn.momentum is not None else 0.0, bn.eps, bool(with_pool), torch.is_grad_enabled())
     y, packed = out[0], out[-1]
     _PREPACKED["src"], _PREPACKED["packed"] = weakref.ref(y), packed
     return (y, out[1]) if with_pool else y
