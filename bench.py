@@ -353,9 +353,9 @@ def roofline(kms, peaks, net):
                     "frac": ach / peaks["bf16_tflops_sustained"], "algorithmic_flops": fwd_flops, "algorithmic_bytes": nbytes,
                     "hbm_achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "peak_source": peaks["source"] + " (sustained bf16)",
-                    "traffic": _ncu_traffic("r1_fused_query_fwd_v2.txt", "fused_query_kernel"),
-                    "traffic_note": "dram read+write per launch, ncu --set full of the same kernel in inference mode "
-                                    "(profiles/r1_fused_query_fwd_v2.txt); the training launch adds the saved features/activations"})
+                    "traffic": _ncu_traffic("r1_query_path_v3.txt", "fused_query_kernel"),
+                    "traffic_note": "dram read+write per launch, ncu --set full of the same training launch "
+                                    "(profiles/r1_query_path_v3.txt)"})
     elif name in ("svr_gather_fwd", "svr_gather_bwd"):
         # gather: volumes + grid in, feature rows out; scatter: d-feature rows in, fp32 gradient volumes written once
         nbytes = (vols_bf16 + x_bytes + M * 12 + M * kp * 2) if name == "svr_gather_fwd" else (M * kp * 2 + 2 * vols_bf16 + M * 12)

@@ -239,6 +239,9 @@ int svr_conv1_relu_bn_bwd(const float *x, const float *w, const float *bias, con
  *   svr_relu_bwd_cl  : g = gy * [y > 0] as fp32 (g_f32, nullable) and/or bf16 (g_bf16, nullable); gbias[c] = sum_rows g
  *                      (nullable) from the same pass.                                                             */
 int svr_bias_relu_cl(float *y, const float *bias, int64_t rows, int C, void *stream);
+/* dst[i] = (float) src[i] for a dense bf16 buffer of n elements (n % 8 == 0, 16-byte aligned): widens cuDNN's bf16
+ * backward-data result for the fp32 gradient chain without torch's strided element-wise copy.                     */
+int svr_widen_bf16(const uint16_t *src, int64_t n, float *dst, void *stream);
 size_t svr_relu_bwd_cl_workspace_bytes(int C);
 int svr_relu_bwd_cl(const float *gy, const float *y, int64_t rows, int C, float *g_f32, uint16_t *g_bf16, float *gbias,
                     void *workspace, size_t workspace_bytes, void *stream);

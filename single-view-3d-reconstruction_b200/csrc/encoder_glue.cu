@@ -61,18 +61,34 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float4 *__restrict_
 
 // gb[c] = sum over blocks of partial[block][c]; one warp per 32 channels x 8 block slices
 __global__ void relu_bwd_reduce_kernel(const float *__restrict__ partial, int nblocks, int C, float *__restrict__ gb) {
-    __shared__ float sl[8][32];
-    const int col = threadIdx.x & 31, part = threadIdx.x >> 5;
+    __shared__ float sl[32][33];
+    const int col = threadIdx.x & 31, part = threadIdx.x >> 5;   // 1024 threads: 32 block slices
     const int c = blockIdx.x * 32 + col;
     float v = 0.f;
     if (c < C)
-        for (int b = part; b < nblocks; b += 8) v += partial[(int64_t)b * C + c];
+        for (int b = part; b < nblocks; b += 32) v += partial[(int64_t)b * C + c];
     sl[part][col] = v;
     __syncthreads();
     if (part == 0 && c < C) {
         v = 0.f;
-        for (int k = 0; k < 8; ++k) v += sl[k][col];
+        for (int k = 0; k < 32; ++k) v += sl[k][col];
         gb[c] = v;
+    }
+}
+
+// bf16 -> fp32 of a dense buffer (cuDNN's bf16 backward-data result feeding an fp32 gradient chain)
+__global__ void __launch_bounds__(256) widen_bf16_kernel(const uint4 *__restrict__ src, int64_t n8, float4 *__restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = __uint_as_float(w[k] << 16);
+            f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+        dst[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+        dst[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
     }
 }
 
@@ -95,6 +111,18 @@ int svr_bias_relu_cl(float *y, const float *bias, int64_t rows, int C, void *str
     return 0;
 }
 
+int svr_widen_bf16(const uint16_t *src, int64_t n, float *dst, void *stream) {
+    SVR_REQUIRE(src && dst && n >= 0 && n % 8 == 0, "widen_bf16: element count must be a multiple of 8");
+    SVR_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "widen_bf16: buffers must be 16-byte aligned");
+    if (n == 0) return 0;
+    int64_t blocks = ceil_div<int64_t>(n / 8, 256 * 2);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    widen_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(src), n / 8, reinterpret_cast<float4 *>(dst));
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
 size_t svr_relu_bwd_cl_workspace_bytes(int C) { return (size_t)sm_count() * 8 * C * sizeof(float) + 256; }
 
 int svr_relu_bwd_cl(const float *gy, const float *y, int64_t rows, int C, float *g_f32, uint16_t *g_bf16, float *gbias, void *workspace,
@@ -113,7 +141,7 @@ int svr_relu_bwd_cl(const float *gy, const float *y, int64_t rows, int C, float 
     relu_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(gy), reinterpret_cast<const float4 *>(y), c4, rows,
                                                                        reinterpret_cast<float4 *>(g_f32), reinterpret_cast<uint2 *>(g_bf16),
                                                                        reinterpret_cast<float4 *>(workspace));
-    if (gbias) relu_bwd_reduce_kernel<<<ceil_div(C, 32), 256, 0, as_stream(stream)>>>((const float *)workspace, (int)blocks, C, gbias);
+    if (gbias) relu_bwd_reduce_kernel<<<ceil_div(C, 32), 1024, 0, as_stream(stream)>>>((const float *)workspace, (int)blocks, C, gbias);
     SVR_LAUNCH_CHECK();
     return 0;
 }

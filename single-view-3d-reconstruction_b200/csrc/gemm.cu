@@ -403,16 +403,25 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float *__restrict__
 
 __global__ void head_bwd_reduce_kernel(const float *__restrict__ part_w, const float *__restrict__ part_b, int nblocks,
                                        int Hd, float *__restrict__ gwout, float *__restrict__ gbout) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col < Hd) {
-        float v = 0.f;
-        for (int b = 0; b < nblocks; ++b) v += part_w[(int64_t)b * Hd + col];
-        gwout[col] += v;
-    }
-    if (col == 0) {
-        float v = 0.f;
-        for (int b = 0; b < nblocks; ++b) v += part_b[b];
-        gbout[0] += v;
+    // block = 32 columns x 32 block slices (a serial walk over the blocks is a chain of ~300 dependent L2 round trips);
+    // column Hd is the bias partial.  Fixed summation order: deterministic.
+    __shared__ float sl[32][33];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    float v = 0.f;
+    if (col < Hd)
+        for (int b = part; b < nblocks; b += 32) v += part_w[(int64_t)b * Hd + col];
+    else if (col == Hd)
+        for (int b = part; b < nblocks; b += 32) v += part_b[b];
+    sl[part][lane] = v;
+    __syncthreads();
+    if (part == 0 && col <= Hd) {
+        v = 0.f;
+        for (int k = 0; k < 32; ++k) v += sl[k][lane];
+        if (col < Hd)
+            gwout[col] += v;
+        else
+            gbout[0] += v;
     }
 }
 
@@ -453,11 +462,19 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
 
 __global__ void colsum_reduce_kernel(const float *__restrict__ part, int nblocks, int N, float *__restrict__ out,
                                      int accumulate) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= N) return;
+    __shared__ float sl[32][33];     // 32 columns x 32 block slices, fixed summation order
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
     float v = 0.f;
-    for (int b = 0; b < nblocks; ++b) v += part[(int64_t)b * N + col];
-    out[col] = accumulate ? out[col] + v : v;
+    if (col < N)
+        for (int b = slice; b < nblocks; b += 32) v += part[(int64_t)b * N + col];
+    sl[slice][lane] = v;
+    __syncthreads();
+    if (slice == 0 && col < N) {
+        v = 0.f;
+        for (int k = 0; k < 32; ++k) v += sl[k][lane];
+        out[col] = accumulate ? out[col] + v : v;
+    }
 }
 
 __global__ void pack_matrix_kernel(const float *__restrict__ w, int R, int C, __nv_bfloat16 *__restrict__ wp,
@@ -575,7 +592,7 @@ int svr_decoder_head_bwd(const float *dlogit, const int *perm, const uint16_t *h
     if (int rc = scratch_alloc(&scratch, (size_t)nblocks * (Hd + 1), st)) return rc;
     head_bwd_kernel<<<nblocks, 256, 0, st>>>(dlogit, perm, (const __nv_bfloat16 *)h2, wout, M, Hd, (__nv_bfloat16 *)dz2, scratch,
                                              scratch + (size_t)nblocks * Hd, rows_per_block);
-    head_bwd_reduce_kernel<<<ceil_div(Hd, 256), 256, 0, st>>>(scratch, scratch + (size_t)nblocks * Hd, nblocks, Hd, gwout, gbout);
+    head_bwd_reduce_kernel<<<ceil_div(Hd + 1, 32), 1024, 0, st>>>(scratch, scratch + (size_t)nblocks * Hd, nblocks, Hd, gwout, gbout);
     SVR_LAUNCH_CHECK();
     SVR_CUDA(cudaFreeAsync(scratch, st));
     return 0;
@@ -594,7 +611,7 @@ int svr_colsum_bf16(const uint16_t *a, int M, int N, int64_t lda, float *out, in
     if (int rc = scratch_alloc(&scratch, (size_t)nblocks * N, st)) return rc;
     colsum_partial_kernel<<<dim3(ceil_div(N, 256), nblocks), 256, 0, st>>>((const __nv_bfloat16 *)a, M, N, lda, rows_per_block,
                                                                           scratch);
-    colsum_reduce_kernel<<<ceil_div(N, 256), 256, 0, st>>>(scratch, nblocks, N, out, accumulate);
+    colsum_reduce_kernel<<<ceil_div(N, 32), 1024, 0, st>>>(scratch, nblocks, N, out, accumulate);
     SVR_LAUNCH_CHECK();
     SVR_CUDA(cudaFreeAsync(scratch, st));
     return 0;

@@ -345,7 +345,7 @@ class _ConvBf16Backward(torch.autograd.Function):
         gx, gw, _ = torch.ops.aten.convolution_backward(g_bf, x_bf, w_bf, None, list(stride), list(padding), list(dilation), False, [0, 0, 0],
                                                         groups, [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         gb = gy.sum((0, 2, 3, 4)) if has_bias and ctx.needs_input_grad[2] else None
-        return (gx.float() if gx is not None else None, gw.to(weight.dtype) if gw is not None else None, gb, None, None, None, None)
+        return (_widen_bf16(gx) if gx is not None else None, gw.to(weight.dtype) if gw is not None else None, gb, None, None, None, None)
 
 
 class _ConvBiasReLU(torch.autograd.Function):
@@ -391,7 +391,7 @@ class _ConvBiasReLU(torch.autograd.Function):
         gx, gw, _ = torch.ops.aten.convolution_backward(g, xs, w, None, list(stride), list(padding), list(dilation), False, [0, 0, 0], groups,
                                                         [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         if gx is not None and gx.dtype != torch.float32:
-            gx = gx.float()
+            gx = _widen_bf16(gx)
         if gw is not None and gw.dtype != weight.dtype:
             gw = gw.to(weight.dtype)
         return gx, gw, gb, None, None, None, None, None
@@ -407,6 +407,18 @@ def _to_bf16_channels_last(x):
     if x.dtype == torch.float32 and x.is_cuda and x.dim() == 5 and x.is_contiguous(memory_format=torch.channels_last_3d):
         return pack_volume(x).permute(0, 4, 1, 2, 3)
     return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+
+
+def _widen_bf16(t):
+    """fp32 copy of a dense bf16 tensor with the same strides (vectorised; torch's .float() on a channels-last view is a
+    strided element-wise copy)."""
+    if (t.dtype == _BF16 and t.is_cuda and t.numel() % 8 == 0 and t.data_ptr() % 16 == 0
+            and (t.is_contiguous() or (t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d)))):
+        out = torch.empty_like(t, dtype=torch.float32)          # preserve_format: same dense strides
+        if out.stride() == t.stride():
+            _abi.check(_lib().svr_widen_bf16(t.data_ptr(), t.numel(), out.data_ptr(), _stream()), "widen_bf16")
+            return out
+    return t.float()
 
 
 def conv3d_bf16_backward(x, conv):

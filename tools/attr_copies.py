@@ -31,8 +31,11 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 rows = []
 for e in prof.events():
-    if e.name in ("aten::copy_", "aten::fill_", "aten::add", "aten::add_", "aten::zero_", "aten::contiguous", "aten::sum", "aten::clone") and e.device_time_total > 15:
-        stack = [s for s in e.stack if "svr" in s or "single-view" in s or "bench" in s or "tools/" in s][:3]
-        rows.append((e.device_time_total, e.name, str(e.input_shapes)[:90], " <- ".join(s.split("/")[-1][:70] for s in stack)))
+    if e.name in ("aten::copy_", "aten::fill_", "aten::add", "aten::add_", "aten::zero_", "aten::contiguous", "aten::sum", "aten::clone", "aten::to", "aten::_to_copy") and e.device_time_total > 15:
+        chain, q = [], e.cpu_parent
+        while q is not None and len(chain) < 5:
+            chain.append(q.name)
+            q = q.cpu_parent
+        rows.append((e.device_time_total, e.name, str(e.input_shapes)[:70], " <- ".join(chain)))
 for r in sorted(rows, reverse=True)[:40]:
     print(f"{r[0]:8.1f} us  {r[1]:16s} {r[2]:90s} {r[3]}")
