@@ -7,6 +7,7 @@ from . import _abi, ops  # noqa: F401
 from .model.ifnet import (IFNet, IFNetFeatureExtractor, IFNetFeatureExtractor128, configure, evaluate_network_on_grid,  # noqa: F401
                           implicit_to_mesh, make_3d_grid)
 from .model.projection import project  # noqa: F401
+from .prefetch import HostPrefetcher  # noqa: F401
 
 __all__ = ["IFNet", "IFNetFeatureExtractor", "IFNetFeatureExtractor128", "configure", "evaluate_network_on_grid",
-           "implicit_to_mesh", "make_3d_grid", "project", "ops"]
+           "implicit_to_mesh", "make_3d_grid", "project", "ops", "HostPrefetcher"]
