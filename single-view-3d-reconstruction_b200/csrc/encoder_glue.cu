@@ -99,10 +99,11 @@ using namespace svr;
 extern "C" {
 
 int svr_bias_relu_cl(float *y, const float *bias, int64_t rows, int C, void *stream) {
-    SVR_REQUIRE(y, "bias_relu_cl: null pointer");
     SVR_REQUIRE(C > 0 && C % 4 == 0 && 256 % (C / 4) == 0, "bias_relu_cl: channel count must be 4, 8, ..., 1024 with 256 %% (C/4) == 0 (got %d)", C);
+    SVR_REQUIRE(rows >= 0, "bias_relu_cl: negative row count");
     const int64_t n4 = rows * (C / 4);
     if (n4 == 0) return 0;
+    SVR_REQUIRE(y, "bias_relu_cl: null pointer");
     int64_t blocks = ceil_div<int64_t>(n4, 256 * 4);
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
@@ -112,9 +113,10 @@ int svr_bias_relu_cl(float *y, const float *bias, int64_t rows, int C, void *str
 }
 
 int svr_widen_bf16(const uint16_t *src, int64_t n, float *dst, void *stream) {
-    SVR_REQUIRE(src && dst && n >= 0 && n % 8 == 0, "widen_bf16: element count must be a multiple of 8");
-    SVR_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "widen_bf16: buffers must be 16-byte aligned");
+    SVR_REQUIRE(n >= 0 && n % 8 == 0, "widen_bf16: element count must be a non-negative multiple of 8");
     if (n == 0) return 0;
+    SVR_REQUIRE(src && dst, "widen_bf16: null pointer");
+    SVR_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "widen_bf16: buffers must be 16-byte aligned");
     int64_t blocks = ceil_div<int64_t>(n / 8, 256 * 2);
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
@@ -127,13 +129,14 @@ size_t svr_relu_bwd_cl_workspace_bytes(int C) { return (size_t)sm_count() * 8 * 
 
 int svr_relu_bwd_cl(const float *gy, const float *y, int64_t rows, int C, float *g_f32, uint16_t *g_bf16, float *gbias, void *workspace,
                     size_t workspace_bytes, void *stream) {
-    SVR_REQUIRE(gy && y && workspace && (g_f32 || g_bf16), "relu_bwd_cl: null pointer");
     SVR_REQUIRE(C > 0 && C % 4 == 0 && 256 % (C / 4) == 0, "relu_bwd_cl: channel count must be 4, 8, ..., 1024 with 256 %% (C/4) == 0 (got %d)", C);
-    SVR_REQUIRE(workspace_bytes >= svr_relu_bwd_cl_workspace_bytes(C), "relu_bwd_cl: workspace too small");
+    SVR_REQUIRE(rows >= 0, "relu_bwd_cl: negative row count");
     if (rows == 0) {
         if (gbias) SVR_CUDA(cudaMemsetAsync(gbias, 0, C * sizeof(float), as_stream(stream)));
         return 0;
     }
+    SVR_REQUIRE(gy && y && workspace && (g_f32 || g_bf16), "relu_bwd_cl: null pointer");
+    SVR_REQUIRE(workspace_bytes >= svr_relu_bwd_cl_workspace_bytes(C), "relu_bwd_cl: workspace too small");
     const int c4 = C / 4, rpb = 256 / c4;
     int64_t blocks = ceil_div<int64_t>(rows, rpb * 4);
     const int64_t cap = (int64_t)sm_count() * 8;
