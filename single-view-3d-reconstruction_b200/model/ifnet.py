@@ -39,6 +39,12 @@ if not hasattr(args, "channels_last"):
     args.channels_last = True
 
 
+# Layers with at least this many input voxels (batch x D x H x W) use cuDNN's bf16 backward kernels when
+# args.bf16_conv_backward is set: the 64^3 and 32^3 layers at batch 4 (tools/conv_probe.py: wgrad 0.62-0.89 -> 0.22-0.34 ms
+# and 0.09 -> 0.06 ms per layer); below that the casts cost more than the kernels gain.
+BF16_BACKWARD_MIN_VOXELS = 1 << 17
+
+
 def configure(**kw):
     """Override module-level settings (net_res, inf_res, num_points, batch_size)."""
     for k, v in kw.items():
@@ -87,7 +93,7 @@ class _ExtractorBase(nn.Module):
         operands (``args.bf16_conv_backward``, see ops._ConvBf16Backward) while the forward stays fp32/TF32."""
         if (getattr(args, "bf16_conv_backward", True) and getattr(args, "channels_last", False) and x.is_cuda and x.dtype == torch.float32
                 and torch.is_grad_enabled() and conv.weight.requires_grad and conv.padding_mode == "zeros"
-                and x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= (1 << 20)):
+                and x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= BF16_BACKWARD_MIN_VOXELS):
             return ops.conv3d_bf16_backward(x, conv)
         return conv(x)
 
@@ -98,7 +104,7 @@ class _ExtractorBase(nn.Module):
         if (getattr(args, "channels_last", False) and getattr(args, "fuse_conv_relu", True) and x.is_cuda and x.dtype == torch.float32
                 and conv.weight.dtype == torch.float32 and conv.padding_mode == "zeros" and co % 4 == 0 and 256 % (co // 4) == 0
                 and x.is_contiguous(memory_format=torch.channels_last_3d)):
-            big = x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= (1 << 20)
+            big = x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= BF16_BACKWARD_MIN_VOXELS
             return ops.conv3d_bias_relu(x, conv, bool(getattr(args, "bf16_conv_backward", True) and big))
         return self.actvn(self._conv(conv, x))
 
