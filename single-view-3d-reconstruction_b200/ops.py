@@ -719,6 +719,10 @@ class _Query(torch.autograd.Function):
 
 
 def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols):
+    if points.shape[0] * points.shape[1] == 0:          # empty query set: nothing to launch (ifnet.py:38-61 returns (B, 0))
+        if not points.is_cuda:
+            raise RuntimeError("svr_b200: `points` must be a CUDA tensor; there is no CPU path")
+        return points.new_zeros((points.shape[0], points.shape[1]), dtype=torch.float32)
     return _Query.apply(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
 
 
@@ -757,6 +761,10 @@ class _Gather(torch.autograd.Function):
 
 
 def gather(pyr, points, x, vols):
+    if points.shape[0] * points.shape[1] == 0:
+        if not points.is_cuda:
+            raise RuntimeError("svr_b200: `points` must be a CUDA tensor; there is no CPU path")
+        return torch.zeros((0, pyr.kp), device=points.device, dtype=_BF16)
     return _Gather.apply(pyr, points, x, *vols)
 
 

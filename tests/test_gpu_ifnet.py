@@ -425,3 +425,20 @@ def test_conv_bias_relu_fused(bf16_backward):
     assert rel(xa.grad, xb.grad) < tol, rel(xa.grad, xb.grad)
     assert rel(conv.weight.grad, ref.weight.grad) < tol, rel(conv.weight.grad, ref.weight.grad)
     assert rel(conv.bias.grad, ref.bias.grad) < 2e-3
+
+
+@pytest.mark.parametrize("n_points", [0, 1, 127, 129])
+def test_query_ragged_point_counts(golden, n_points):
+    """Empty and ragged query sets (not a multiple of the 128-row tile): shapes, finiteness, and agreement with the same
+    points evaluated inside a larger batch (rows are independent)."""
+    g, sd = _case(golden, 128)
+    net = _net(128, sd).eval()
+    x = torch.from_numpy(g["x"]).cuda()
+    pts = torch.from_numpy(g["pts"]).cuda()
+    with torch.no_grad():
+        full = net(x, pts)
+        part = net(x, pts[:, :n_points].contiguous())
+    assert part.shape == (x.shape[0], n_points)
+    if n_points:
+        assert torch.isfinite(part).all()
+        assert float((part - full[:, :n_points]).abs().max()) <= 1e-6 * max(1.0, float(full.abs().max()))
