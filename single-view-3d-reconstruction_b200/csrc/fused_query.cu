@@ -180,6 +180,25 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 const int u = kc * 8 + unit_in_chunk;
                 UnitCtx uc;
                 make_unit_ctx_packed(p.P, s.utab[u], p.vols.v, uc);
+                // compile-time specialised gather for the 128-net's levels (uniform over the chunk's threads per unit)
+                int spec = 0;
+                if (!p.P.align && uc.real && uc.level > 0 && uc.W == uc.H && uc.H == uc.D) {
+                    if (uc.W == 128 && uc.C == 16) spec = 1;
+                    else if (uc.W == 64 && uc.C == 32) spec = 2;
+                    else if (uc.W == 32 && uc.C == 64) spec = 3;
+                    else if (uc.W == 16 && uc.C == 128) spec = 4;
+                    else if (uc.W == 8 && uc.C == 128) spec = 5;
+                }
+                auto gather_one = [&](float qx, float qy, float qz, int scene) -> uint4 {
+                    switch (spec) {
+                        case 1: return gather_unit_fast_c<128, 16>(uc, qx, qy, qz, scene);
+                        case 2: return gather_unit_fast_c<64, 32>(uc, qx, qy, qz, scene);
+                        case 3: return gather_unit_fast_c<32, 64>(uc, qx, qy, qz, scene);
+                        case 4: return gather_unit_fast_c<16, 128>(uc, qx, qy, qz, scene);
+                        case 5: return gather_unit_fast_c<8, 128>(uc, qx, qy, qz, scene);
+                        default: return gather_unit_fast(uc, p.P.align, qx, qy, qz, scene);
+                    }
+                };
                 mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
                 uint8_t *a_st = s.a + st * FQ_A_BYTES;
 #pragma unroll 2
@@ -202,9 +221,9 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                         if (unit_in_chunk == 0)
                             val = float8_to_bf16(v8);
                         else if (uc.real && uc.level > 0 && scene >= 0)
-                            val = gather_unit_fast(uc, p.P.align, q.x, q.y, q.z, scene);
+                            val = gather_one(q.x, q.y, q.z, scene);
                     } else if (uc.real && scene >= 0) {
-                        val = gather_unit_fast(uc, p.P.align, q.x, q.y, q.z, scene);
+                        val = gather_one(q.x, q.y, q.z, scene);
                     }
                     *reinterpret_cast<uint4 *>(a_st + swz128(r, unit_in_chunk)) = val;
                     if (p.save_feat) {

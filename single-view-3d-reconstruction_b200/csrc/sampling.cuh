@@ -334,6 +334,72 @@ __device__ __forceinline__ uint4 gather_unit_fast(const UnitCtx &c, int align, f
     }
     return make_uint4(out[0], out[1], out[2], out[3]);
 }
+// gather_unit_fast specialised at compile time for a cubic grid of LW^3 voxels with LC channels and align_corners = False
+// (the five sampled levels of the 128-net): sizes, strides and the 8 corner offsets become immediates, the index
+// products become shifts.  Same arithmetic, same bits.
+template <int LW, int LC>
+__device__ __forceinline__ uint4 gather_unit_fast_c(const UnitCtx &c, float px, float py, float pz, int scene) {
+    constexpr int align = 0;
+    constexpr float fLW = (float)LW;
+    constexpr int cW = LW, cH = LW, cD = LW, cC = LC, c_sy = LW * LC, c_sz = LW * LW * LC;
+    constexpr int64_t c_scene = (int64_t)LW * LW * LW * LC;
+    constexpr bool c_coarse = LW <= 16;
+    // q = 2*p + displacement: 2*p is exact, so the fused form rounds exactly like the reference's mul + add
+    const float ix = unnorm(__fadd_rn(__fmul_rn(2.0f, pz), c.dx), fLW, align);
+    const float iy = unnorm(__fadd_rn(__fmul_rn(2.0f, py), c.dy), fLW, align);
+    const float iz = unnorm(__fadd_rn(__fmul_rn(2.0f, px), c.dz), fLW, align);
+    float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    fx = fminf(fmaxf(fx, -4.0f), fLW + 2.0f);
+    fy = fminf(fmaxf(fy, -4.0f), fLW + 2.0f);
+    fz = fminf(fmaxf(fz, -4.0f), fLW + 2.0f);
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+    const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+    const float wz1 = iz - fz, wz0 = (fz + 1.0f) - iz;
+    const __nv_bfloat16 *ptr = c.base + (int64_t)scene * c_scene + ((z0 * cH + y0) * cW + x0) * cC;
+    const bool interior = x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + 1 < cW && y0 + 1 < cH && z0 + 1 < cD;
+    uint4 raw[8];
+    float w[8];
+    const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+    if (interior && !c_coarse) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int off = ((k & 1) ? cC : 0) + ((k & 2) ? c_sy : 0) + ((k & 4) ? c_sz : 0);
+            raw[k] = __ldg(reinterpret_cast<const uint4 *>(ptr + off));
+            w[k] = wxy[k & 3] * ((k & 4) ? wz1 : wz0);
+        }
+    } else {
+#pragma unroll
+        const bool vx[2] = {(unsigned)x0 < (unsigned)cW, (unsigned)(x0 + 1) < (unsigned)cW};
+        const bool vy[2] = {(unsigned)y0 < (unsigned)cH, (unsigned)(y0 + 1) < (unsigned)cH};
+        const bool vz[2] = {(unsigned)z0 < (unsigned)cD, (unsigned)(z0 + 1) < (unsigned)cD};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool in = vx[k & 1] && vy[(k >> 1) & 1] && vz[k >> 2];
+            const int off = ((k & 1) ? cC : 0) + ((k & 2) ? c_sy : 0) + ((k & 4) ? c_sz : 0);
+            raw[k] = in ? __ldg(reinterpret_cast<const uint4 *>(ptr + off)) : make_uint4(0, 0, 0, 0);
+            w[k] = in ? wxy[k & 3] * ((k & 4) ? wz1 : wz0) : 0.f;
+        }
+    }
+    unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        ffma2(acc[0], raw[k].x, w[k]);
+        ffma2(acc[1], raw[k].y, w[k]);
+        ffma2(acc[2], raw[k].z, w[k]);
+        ffma2(acc[3], raw[k].w, w[k]);
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        out[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace svr
