@@ -386,6 +386,13 @@ def roofline(kms, peaks, net):
         ach = nbytes / (ms * 1e-3) / 1e9
         out.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                     "algorithmic_bytes": nbytes})
+        if name == "svr_gather_bwd":       # one call = tensor-core scatter (coarse levels) + direct scatter (fine levels)
+            parts = [_ncu_traffic("r1_query_path_v3.txt", k) for k in ("scatter_tc_kernel", "gather_bwd_kernel")]
+            if all(v is not None for v in parts):
+                out["traffic"] = sum(parts)
+                out["traffic_note"] = ("dram read+write of scatter_tc_kernel + gather_bwd_kernel, ncu --set full of the same training step "
+                                       "(profiles/r1_query_path_v3.txt); above the algorithmic bytes because the fp32 gradient volumes are "
+                                       "read-modify-written by the L2 atomic units")
     else:
         flops = fwd_flops   # backward-data (dz1, dz0, dfeat) resp. weight-gradient (dW2, dW1, dW0) GEMMs: one forward's worth each
         ach = flops / (ms * 1e-3) / 1e12
