@@ -38,6 +38,7 @@ constexpr int CB_DS = 24;                 // stride of a parked gradient row (16
 struct CbGeom {
     int B, D, H, W, segs_per_row, n_segs;
     int64_t n_vox;
+    int pow2, sh_spr, sh_h, sh_d;     // segs_per_row, H and D powers of two: segment decode by shifts instead of divisions
 };
 
 typedef unsigned long long f32x2;
@@ -98,8 +99,18 @@ struct CbSeg {
 // outside the volume) and commits them as one cp.async group.  The caller must have passed a __syncwarp since the
 // last reader of `tile`.
 __device__ __forceinline__ CbSeg cb_decode(const CbGeom &g, int seg) {
-    const int row = seg / g.segs_per_row;
     CbSeg sg;
+    if (g.pow2) {
+        const int row = seg >> g.sh_spr;
+        sg.x0 = (seg & (g.segs_per_row - 1)) * CB_SEG;
+        sg.yy = row & (g.H - 1);
+        const int r2 = row >> g.sh_h;
+        sg.zz = r2 & (g.D - 1);
+        sg.b = r2 >> g.sh_d;
+        sg.p0 = (((int64_t)sg.b * g.D + sg.zz) * g.H + sg.yy) * g.W + sg.x0;
+        return sg;
+    }
+    const int row = seg / g.segs_per_row;
     sg.x0 = (seg - row * g.segs_per_row) * CB_SEG;
     sg.yy = row % g.H;
     const int r2 = row / g.H;
@@ -691,6 +702,16 @@ static bool cb_geom(CbGeom &g, int B, int D, int H, int W) {
     g.n_vox = (int64_t)B * D * H * W;
     if (n >= ((int64_t)1 << 31)) return false;
     g.n_segs = (int)n;
+    auto log2i = [](int v) {
+        int l = 0;
+        while ((1 << l) < v) ++l;
+        return l;
+    };
+    auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    g.pow2 = is_pow2(g.segs_per_row) && is_pow2(H) && is_pow2(D) ? 1 : 0;
+    g.sh_spr = log2i(g.segs_per_row);
+    g.sh_h = log2i(H);
+    g.sh_d = log2i(D);
     return true;
 }
 
