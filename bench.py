@@ -377,9 +377,9 @@ def roofline(kms, peaks, net):
                     "frac": ach / peaks["bf16_tflops_sustained"], "algorithmic_flops": fwd_flops, "algorithmic_bytes": nbytes,
                     "hbm_achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "peak_source": peaks["source"] + " (sustained bf16)",
-                    "traffic": _ncu_traffic("r1_query_path_v3.txt", "fused_query_kernel"),
+                    "traffic": _ncu_traffic("r1_query_path_v4.txt", "fused_query_kernel"),
                     "traffic_note": "dram read+write per launch, ncu --set full of the same training launch "
-                                    "(profiles/r1_query_path_v3.txt)"})
+                                    "(profiles/r1_query_path_v4.txt)"})
     elif name in ("svr_gather_fwd", "svr_gather_bwd"):
         # gather: volumes + grid in, feature rows out; scatter: d-feature rows in, fp32 gradient volumes written once
         nbytes = (vols_bf16 + x_bytes + M * 12 + M * kp * 2) if name == "svr_gather_fwd" else (M * kp * 2 + 2 * vols_bf16 + M * 12)
@@ -387,11 +387,11 @@ def roofline(kms, peaks, net):
         out.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                     "algorithmic_bytes": nbytes})
         if name == "svr_gather_bwd":       # one call = tensor-core scatter (coarse levels) + direct scatter (fine levels)
-            parts = [_ncu_traffic("r1_query_path_v3.txt", k) for k in ("scatter_tc_kernel", "gather_bwd_kernel")]
+            parts = [_ncu_traffic("r1_query_path_v4.txt", k) for k in ("scatter_tc_kernel", "gather_bwd_kernel")]
             if all(v is not None for v in parts):
                 out["traffic"] = sum(parts)
                 out["traffic_note"] = ("dram read+write of scatter_tc_kernel + gather_bwd_kernel, ncu --set full of the same training step "
-                                       "(profiles/r1_query_path_v3.txt); above the algorithmic bytes because the fp32 gradient volumes are "
+                                       "(profiles/r1_query_path_v4.txt); above the algorithmic bytes because the fp32 gradient volumes are "
                                        "read-modify-written by the L2 atomic units")
     else:
         flops = fwd_flops   # backward-data (dz1, dz0, dfeat) resp. weight-gradient (dW2, dW1, dW0) GEMMs: one forward's worth each
