@@ -198,9 +198,6 @@ typedef struct svr_decoder_weights {
 /* bf16 row-major (R, K) -> K/64 chunks of (R x 128 B) in the 128B-swizzled K-major UMMA layout   */
 int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *image, void *stream);
 
-/* diagnostics only: tiles per (level, gather mode: 0 CUDA-core, 1 tensor-core) since the last reset */
-int svr_debug_fq_modes(unsigned long long *out_host, int reset);
-
 int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, const float *x0,
                         const uint16_t *const *vols_host, const svr_pyramid *pyr_host,
                         const svr_decoder_weights *w_host, float *logits, uint16_t *save_h,

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cstring>
+#include <mutex>
 
 namespace svr {
 
@@ -25,6 +26,44 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+bool DeviceOnce::needed(int &dev) {
+    dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 256) return true;   // unknown device: always (re)apply
+    return ((__atomic_load_n(&bits[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) == 0;
+}
+
+void DeviceOnce::done(int dev) {
+    if (dev >= 0 && dev < 256) __atomic_fetch_or(&bits[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+}
+
+int scratch_alloc(void **ptr, size_t bytes, cudaStream_t st) {
+    // Freed scratch stays in the pool (release threshold = max): with the default threshold a pool returns its memory
+    // to the OS at every synchronisation and the next allocation re-maps it (milliseconds).  The pool is ours, one per
+    // device, so the host application's default pool keeps its own settings.
+    static cudaMemPool_t pools[256] = {};
+    static std::mutex mu;
+    int dev = 0;
+    SVR_CUDA(cudaGetDevice(&dev));
+    SVR_REQUIRE(dev >= 0 && dev < 256, "scratch_alloc: device index %d out of range", dev);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            SVR_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+            uint64_t keep = ~0ull;
+            SVR_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = pools[dev];
+    }
+    SVR_CUDA(cudaMallocFromPoolAsync(ptr, bytes, pool, st));
+    return 0;
 }
 
 int make_tmap_bf16_sw128(TensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {

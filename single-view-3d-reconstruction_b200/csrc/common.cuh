@@ -46,6 +46,18 @@ static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 int sm_count();   // cached per device
 
+// One-time per-DEVICE initialisation (cudaFuncSetAttribute is a per-device setting, a process may drive several
+// GPUs): `if (once.needed(dev)) { ...set attributes...; once.done(dev); }`.  Thread-safe; setting an attribute
+// twice from two racing threads is harmless.
+struct DeviceOnce {
+    unsigned long long bits[4] = {0, 0, 0, 0};   // up to 256 devices
+    bool needed(int &dev);
+    void done(int dev);
+};
+
+// stream-ordered scratch from a PRIVATE per-device memory pool (the host application's default pool is left alone)
+int scratch_alloc(void **ptr, size_t bytes, cudaStream_t st);
+
 // 128-byte opaque TMA descriptor (same layout and alignment as the driver's CUtensorMap)
 struct alignas(64) TensorMap {
     uint64_t opaque[16];

@@ -719,13 +719,14 @@ constexpr size_t CB_SMEM = sizeof(CbShared);
 constexpr size_t CB_SMEM_WGRAD = sizeof(CbShared) + (size_t)CB_WARPS * CB_SEG * CB_DS * sizeof(float);
 
 static int cb_attrs() {
-    static bool done = false;
-    if (!done) {
+    static DeviceOnce once;
+    int dev;
+    if (once.needed(dev)) {
         SVR_CUDA(cudaFuncSetAttribute(cb_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
         SVR_CUDA(cudaFuncSetAttribute(cb_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
         SVR_CUDA(cudaFuncSetAttribute(cb_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
         SVR_CUDA(cudaFuncSetAttribute(cb_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM_WGRAD));
-        done = true;
+        once.done(dev);
     }
     return 0;
 }

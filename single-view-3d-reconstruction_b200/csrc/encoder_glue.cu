@@ -9,6 +9,9 @@
 
 namespace svr {
 
+// torch's ReLU (clamp_min / threshold) propagates NaN; fmaxf would turn it into 0 and hide a divergence
+__device__ __forceinline__ float relu_nan(float v) { return v > 0.f ? v : (v != v ? v : 0.f); }
+
 __global__ void __launch_bounds__(256) bias_relu_kernel(float4 *__restrict__ y, const float *__restrict__ bias, int c4, int64_t n4) {
     extern __shared__ float4 b_s[];
     for (int i = threadIdx.x; i < c4; i += blockDim.x) b_s[i] = bias ? reinterpret_cast<const float4 *>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -19,10 +22,10 @@ __global__ void __launch_bounds__(256) bias_relu_kernel(float4 *__restrict__ y, 
     const float4 b = b_s[i0 % c4];
     for (int64_t i = i0; i < n4; i += stride) {
         float4 v = y[i];
-        v.x = fmaxf(v.x + b.x, 0.f);
-        v.y = fmaxf(v.y + b.y, 0.f);
-        v.z = fmaxf(v.z + b.z, 0.f);
-        v.w = fmaxf(v.w + b.w, 0.f);
+        v.x = relu_nan(v.x + b.x);
+        v.y = relu_nan(v.y + b.y);
+        v.z = relu_nan(v.z + b.z);
+        v.w = relu_nan(v.w + b.w);
         y[i] = v;
     }
 }

@@ -298,10 +298,11 @@ extern "C" int svr_decoder_bwd_fused(const uint16_t *dz2, const uint16_t *h1, co
     SVR_REQUIRE(dz2 && h1 && h0 && w2t_img && w1t_img && w0pt_img && dz1 && dz0 && dfeat, "decoder_bwd_fused: null pointer");
     SVR_REQUIRE(kp > 0 && kp % 64 == 0, "decoder_bwd_fused: KP must be a positive multiple of 64");
     if (M == 0) return 0;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce once;
+    int dev;
+    if (once.needed(dev)) {
         SVR_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
-        attr = true;
+        once.done(dev);
     }
     FbParams p;
     if (make_tmap_bf16_sw128(&p.tm_dz2, dz2, M, FB_HID, FB_HID, FB_TILE)) return -1;

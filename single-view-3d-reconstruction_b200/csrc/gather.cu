@@ -3,7 +3,6 @@
 // and their autograd backward (grid_sampler_3d_backward).
 #include "common.cuh"
 #include "sampling.cuh"
-#include <cstdlib>
 
 namespace svr {
 
@@ -163,269 +162,6 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
             const int64_t last = __shfl_sync(0xffffffffu, pt, 31);
             if (lane == 0 && va != 0.f) atomicAdd(gpoints + first * 3 + a, va);
             if (lane == 31 && last != first && vb != 0.f) atomicAdd(gpoints + last * 3 + a, vb);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Tile-aggregated scatter-add for the coarse levels.  Rows arrive spatially sorted (svr_sort_points),
-// so the 128 rows x 7 stencil samples of a tile touch a small box of voxels.  Per tile and level:
-//   1. bounding box of the touched voxels (integer min/max in shared memory);
-//   2. counting sort of the 7168 (sample, corner) contributions by local voxel, placed stencil-point
-//      by stencil-point so that every voxel's segment is ordered by d (integer counters only);
-//   3. for d = 0..6: the d-slice of the tile's d-feature rows (128 x C bf16) is staged ONCE in shared
-//      memory (coalesced), and one thread per (voxel, 8-channel group) walks its segment, blending in
-//      registers with FFMA2 -- every operand comes from shared memory;
-//   4. ONE pair of 16-byte reductions per (voxel, channel group) and tile.
-// Tiles whose box is too large (unsorted input, scene boundary, fine levels) fall back to direct
-// per-contribution reductions for that level.
-// ------------------------------------------------------------------------------------------------
-constexpr int AGG_TILE = 128, AGG_THREADS = 512, AGG_VMAX = 1024, AGG_ROUNDS = 4;
-constexpr int AGG_CONTRIB = AGG_TILE * 7 * 8;
-constexpr int AGG_SLICE_BYTES = AGG_TILE * 128 * 2;     // up to 128 channels
-
-struct AggSmem {
-    float4 pts[AGG_TILE];
-    int box[6];
-    int flags[2];
-    int counts[AGG_VMAX];
-    int start[AGG_VMAX];
-    int cursor[AGG_VMAX];
-    int warp_tot[AGG_THREADS / 32];
-    float w[AGG_CONTRIB];
-    unsigned short rd[AGG_CONTRIB];      // (row << 3) | d
-    uint4 slice[AGG_SLICE_BYTES / 16];   // [row][channel group] of the current stencil point
-};
-
-__global__ void __launch_bounds__(AGG_THREADS) scatter_agg_kernel(const float *__restrict__ points, const int *__restrict__ perm,
-                                                                  int N, int64_t total_rows, Pyr P,
-                                                                  const __nv_bfloat16 *__restrict__ dfeat, GradPtrs gv,
-                                                                  int level_mask) {
-    extern __shared__ uint8_t agg_raw[];
-    AggSmem &S = *reinterpret_cast<AggSmem *>(agg_raw);
-    const int tid = threadIdx.x;
-    const int64_t row0 = (int64_t)blockIdx.x * AGG_TILE;
-    if (tid < AGG_TILE) {
-        int64_t row = row0 + tid;
-        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (row < total_rows) {
-            int64_t pt = perm ? (int64_t)perm[row] : row;
-            q = make_float4(points[pt * 3], points[pt * 3 + 1], points[pt * 3 + 2], __int_as_float((int)(pt / N)));
-        }
-        S.pts[tid] = q;
-    }
-    __syncthreads();
-    const int scene0 = __float_as_int(S.pts[0].w);
-    // thread -> (row, corner pair) for the per-sample passes: all 512 threads busy
-    const int pr = tid & (AGG_TILE - 1), pk = (tid >> 7) * 2;
-
-    for (int level = 1; level < P.n_levels; ++level) {
-        if (!((level_mask >> level) & 1) || !gv.g[level]) continue;   // uniform
-        const int C = P.C[level], W = P.W[level], H = P.H[level], D = P.D[level], ncg = C / 8;
-        const float4 q = S.pts[pr];
-        const int my_scene = __float_as_int(q.w);
-        // ---- bounding box of the in-bounds corners + single-scene test
-        if (tid < 6) S.box[tid] = (tid < 3) ? 0x7fffffff : -0x7fffffff;
-        if (tid == 6) S.flags[0] = 1;
-        __syncthreads();
-        if (tid < AGG_TILE && my_scene >= 0) {
-            if (my_scene != scene0) S.flags[0] = 0;
-            int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
-#pragma unroll
-            for (int d = 0; d < 7; ++d) {
-                Corners c;
-                stencil_corners(P, level, d, q.x, q.y, q.z, c);
-                const int xa = max(c.x0, 0), xb = min(c.x0 + 1, W - 1), ya = max(c.y0, 0), yb = min(c.y0 + 1, H - 1);
-                const int za = max(c.z0, 0), zb = min(c.z0 + 1, D - 1);
-                if (xa <= xb && ya <= yb && za <= zb) {
-                    lo[0] = min(lo[0], xa); lo[1] = min(lo[1], ya); lo[2] = min(lo[2], za);
-                    hi[0] = max(hi[0], xb); hi[1] = max(hi[1], yb); hi[2] = max(hi[2], zb);
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (lo[a] <= hi[a]) {
-                    atomicMin(&S.box[a], lo[a]);
-                    atomicMax(&S.box[3 + a], hi[a]);
-                }
-            }
-        }
-        __syncthreads();
-        const int bx0 = S.box[0], by0 = S.box[1], bz0 = S.box[2];
-        const int nx = S.box[3] - bx0 + 1, ny = S.box[4] - by0 + 1, nz = S.box[5] - bz0 + 1;
-        if (nx <= 0 || ny <= 0 || nz <= 0) {   // nothing in bounds (uniform)
-            __syncthreads();
-            continue;
-        }
-        const int64_t nvox64 = (int64_t)nx * ny * nz;
-        const bool agg = S.flags[0] && scene0 >= 0 && nvox64 <= AGG_VMAX && nvox64 * ncg <= AGG_ROUNDS * AGG_THREADS;
-        const int64_t vol_base = (int64_t)scene0 * D * H * W * C;
-        if (agg) {
-            const int nvox = (int)nvox64;
-            for (int i = tid; i < nvox; i += AGG_THREADS) {
-                S.counts[i] = 0;
-                S.cursor[i] = 0;
-            }
-            __syncthreads();
-            // ---- pass 1: count contributions per local voxel (thread = row x corner pair, loop over d)
-            if (my_scene >= 0) {
-#pragma unroll 1
-                for (int d = 0; d < 7; ++d) {
-                    Corners c;
-                    stencil_corners(P, level, d, q.x, q.y, q.z, c);
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int k = pk + kk;
-                        const int x = c.x0 + (k & 1), y = c.y0 + ((k >> 1) & 1), z = c.z0 + (k >> 2);
-                        if (corner_in(P, level, x, y, z)) atomicAdd(&S.counts[((z - bz0) * ny + (y - by0)) * nx + (x - bx0)], 1);
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- exclusive scan of counts (<= 1024 entries: 2 per thread)
-            {
-                const int lane = tid & 31, warp = tid >> 5;
-                int v[2], sum = 0;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    int i = tid * 2 + j;
-                    v[j] = i < nvox ? S.counts[i] : 0;
-                    sum += v[j];
-                }
-                int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                if (lane == 31) S.warp_tot[warp] = incl;
-                __syncthreads();
-                if (warp == 0) {
-                    int wv = lane < AGG_THREADS / 32 ? S.warp_tot[lane] : 0, wi = wv;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int t = __shfl_up_sync(0xffffffffu, wi, o);
-                        if (lane >= o) wi += t;
-                    }
-                    if (lane < AGG_THREADS / 32) S.warp_tot[lane] = wi - wv;
-                }
-                __syncthreads();
-                int run = S.warp_tot[warp] + incl - sum;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    int i = tid * 2 + j;
-                    if (i < nvox) S.start[i] = run;
-                    run += v[j];
-                }
-            }
-            __syncthreads();
-            // ---- pass 2: place (row, d, weight), one stencil point after the other -> segments sorted by d
-#pragma unroll 1
-            for (int d = 0; d < 7; ++d) {
-                if (my_scene >= 0) {
-                    Corners c;
-                    stencil_corners(P, level, d, q.x, q.y, q.z, c);
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int k = pk + kk;
-                        const int aa = k & 1, bb = (k >> 1) & 1, e = k >> 2;
-                        const int x = c.x0 + aa, y = c.y0 + bb, z = c.z0 + e;
-                        if (!corner_in(P, level, x, y, z)) continue;
-                        const int lid = ((z - bz0) * ny + (y - by0)) * nx + (x - bx0);
-                        const int pos = S.start[lid] + atomicAdd(&S.cursor[lid], 1);
-                        S.rd[pos] = (unsigned short)((pr << 3) | d);
-                        S.w[pos] = c.wx[aa] * c.wy[bb] * c.wz[e];
-                    }
-                }
-                __syncthreads();
-            }
-            // ---- owners: thread <-> up to AGG_ROUNDS (voxel, channel group) tasks, accumulators in registers
-            const int n_tasks = nvox * ncg;
-            unsigned long long acc[AGG_ROUNDS][4];
-            int seg_pos[AGG_ROUNDS], seg_end[AGG_ROUNDS];
-#pragma unroll
-            for (int rr = 0; rr < AGG_ROUNDS; ++rr) {
-                acc[rr][0] = acc[rr][1] = acc[rr][2] = acc[rr][3] = 0ull;
-                const int task = rr * AGG_THREADS + tid;
-                const int vox = task < n_tasks ? task / ncg : 0;
-                seg_pos[rr] = task < n_tasks ? S.start[vox] : 0;
-                seg_end[rr] = task < n_tasks ? S.start[vox] + S.counts[vox] : 0;
-            }
-            const __nv_bfloat16 *tile_rows = dfeat + row0 * P.kp;
-            const int slice_units = AGG_TILE * ncg;
-#pragma unroll 1
-            for (int d = 0; d < 7; ++d) {
-                // stage the d-slice: rows x (ncg x 16 B), coalesced 16-byte loads
-                const int ubase_d = (P.ubase[level] + d * P.upd[level]) * 8;
-                for (int i = tid; i < slice_units; i += AGG_THREADS) {
-                    const int r = i / ncg, cgi = i - r * ncg;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (row0 + r < total_rows) v = __ldg(reinterpret_cast<const uint4 *>(tile_rows + (int64_t)r * P.kp + ubase_d + cgi * 8));
-                    S.slice[i] = v;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int rr = 0; rr < AGG_ROUNDS; ++rr) {
-                    const int task = rr * AGG_THREADS + tid;
-                    const int cg = task % ncg;
-                    int pos = seg_pos[rr];
-                    const int end = seg_end[rr];
-                    while (pos < end) {
-                        const int e = S.rd[pos];
-                        if ((e & 7) != d) break;
-                        const float w = S.w[pos];
-                        const uint4 g = S.slice[(e >> 3) * ncg + cg];
-                        ffma2(acc[rr][0], g.x, w);
-                        ffma2(acc[rr][1], g.y, w);
-                        ffma2(acc[rr][2], g.z, w);
-                        ffma2(acc[rr][3], g.w, w);
-                        ++pos;
-                    }
-                    seg_pos[rr] = pos;
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int rr = 0; rr < AGG_ROUNDS; ++rr) {
-                const int task = rr * AGG_THREADS + tid;
-                if (task >= n_tasks) continue;
-                const int vox = task / ncg, cg = task - vox * ncg;
-                if (S.counts[vox] == 0) continue;
-                float a[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) asm("mov.b64 {%0, %1}, %2;" : "=f"(a[2 * j]), "=f"(a[2 * j + 1]) : "l"(acc[rr][j]));
-                const int lx = vox % nx, ly = (vox / nx) % ny, lz = vox / (nx * ny);
-                float *dst = gv.g[level] + vol_base + (((int64_t)(bz0 + lz) * H + (by0 + ly)) * W + (bx0 + lx)) * C + cg * 8;
-                red_add_v4(dst, a[0], a[1], a[2], a[3]);
-                red_add_v4(dst + 4, a[4], a[5], a[6], a[7]);
-            }
-            __syncthreads();
-        } else {
-            // ---- fallback: direct reductions, one thread per (row, unit of this level)
-            const int units = 7 * ncg;
-            for (int task = tid; task < AGG_TILE * units; task += AGG_THREADS) {
-                const int r = task / units, uu = task - r * units;
-                const int d = uu / ncg, cg = uu - d * ncg;
-                const float4 qq = S.pts[r];
-                const int scene = __float_as_int(qq.w);
-                if (scene < 0) continue;
-                float g[8];
-                bf16x8_to_float(__ldg(reinterpret_cast<const uint4 *>(dfeat + (row0 + r) * P.kp + (int64_t)(P.ubase[level] + uu) * 8)), g);
-                Corners c;
-                stencil_corners(P, level, d, qq.x, qq.y, qq.z, c);
-                const int64_t vb = (int64_t)scene * D * H * W * C + cg * 8;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int aa = k & 1, bb = (k >> 1) & 1, e = k >> 2;
-                    const int x = c.x0 + aa, y = c.y0 + bb, z = c.z0 + e;
-                    if (!corner_in(P, level, x, y, z)) continue;
-                    const float w = c.wx[aa] * c.wy[bb] * c.wz[e];
-                    float *dst = gv.g[level] + vb + (((int64_t)z * H + y) * W + x) * C;
-                    red_add_v4(dst, g[0] * w, g[1] * w, g[2] * w, g[3] * w);
-                    red_add_v4(dst + 4, g[4] * w, g[5] * w, g[6] * w, g[7] * w);
-                }
-            }
-            __syncthreads();
         }
     }
 }
@@ -648,7 +384,7 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
     int64_t total_pts = (int64_t)B * N;
     if (total_pts == 0) return 0;
     // Coarse levels (<= 32^3-class grids: a sorted tile touches a few hundred voxels at most) go through the
-    // tile-aggregated kernel when the rows are spatially sorted (perm given); the fine levels (few
+    // tensor-core scatter (scatter_tc.cu) when the rows are spatially sorted (perm given); the fine levels (few
     // contributions per voxel and tile), level 0 and d(points) stay on the direct kernel.
     int agg_mask = 0;
     if (perm && gvols_host)
@@ -686,22 +422,8 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
                                                                             (const __nv_bfloat16 *)dfeat, gx0, gp, gpoints, direct_mask,
                                                                             u_lo, u_cnt);
     }
-    static int use_tc = -1;
-    if (use_tc < 0) {
-        const char *e = getenv("SVR_SCATTER");
-        use_tc = (e && e[0] == 'a') ? 0 : 1;     // SVR_SCATTER=agg selects the CUDA-core list-walking variant
-    }
-    if (agg_mask && use_tc) {
+    if (agg_mask)
         if (int rc = launch_scatter_tc(points, perm, N, total_pts, P, (const __nv_bfloat16 *)dfeat, gp.g, agg_mask, as_stream(stream))) return rc;
-    } else if (agg_mask) {
-        static bool attr = false;
-        if (!attr) {
-            SVR_CUDA(cudaFuncSetAttribute(scatter_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AggSmem)));
-            attr = true;
-        }
-        scatter_agg_kernel<<<(unsigned)ceil_div<int64_t>(total_pts, AGG_TILE), AGG_THREADS, sizeof(AggSmem), as_stream(stream)>>>(
-            points, perm, N, total_pts, P, (const __nv_bfloat16 *)dfeat, gp, agg_mask);
-    }
     SVR_LAUNCH_CHECK();
     return 0;
 }

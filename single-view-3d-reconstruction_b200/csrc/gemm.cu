@@ -498,31 +498,19 @@ static int tn_splits(int M, int N, int P) {
 }
 
 static int set_gemm_attrs() {
-    static bool done = false;
-    if (done) return 0;
+    static DeviceOnce once;
+    int dev;
+    if (!once.needed(dev)) return 0;
     SVR_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(2)));
     SVR_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(4)));
     SVR_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(4)));
-    done = true;
+    once.done(dev);
     return 0;
 }
 
-// scratch for the head/colsum partials lives in a per-call cudaMallocAsync'd buffer
+// scratch for the head/colsum partials: stream-ordered allocation from the library's private pool (common.cu)
 static int scratch_alloc(float **ptr, size_t n_floats, cudaStream_t st) {
-    // keep freed scratch in the stream-ordered pool: with the default release threshold (0) the pool
-    // returns memory to the OS at every synchronisation and the next allocation re-maps it (milliseconds)
-    static thread_local int pool_dev = -1;
-    int dev = 0;
-    SVR_CUDA(cudaGetDevice(&dev));
-    if (dev != pool_dev) {
-        cudaMemPool_t pool;
-        SVR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = ~0ull;
-        SVR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_dev = dev;
-    }
-    SVR_CUDA(cudaMallocAsync((void **)ptr, n_floats * sizeof(float), st));
-    return 0;
+    return ::svr::scratch_alloc((void **)ptr, n_floats * sizeof(float), st);
 }
 
 }  // namespace svr

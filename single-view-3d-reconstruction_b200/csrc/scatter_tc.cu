@@ -259,10 +259,11 @@ __global__ void __launch_bounds__(ST_THREADS, 2) scatter_tc_kernel(const float *
 
 int launch_scatter_tc(const float *points, const int *perm, int N, int64_t total_rows, const Pyr &P, const __nv_bfloat16 *dfeat,
                       float *const *gvols, int level_mask, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce once;
+    int dev;
+    if (once.needed(dev)) {
         SVR_CUDA(cudaFuncSetAttribute(scatter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        attr = true;
+        once.done(dev);
     }
     StGrad g;
     for (int l = 0; l < SVR_MAX_LEVELS; ++l) g.g[l] = gvols[l];

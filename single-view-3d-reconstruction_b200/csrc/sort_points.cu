@@ -1,7 +1,8 @@
 // Spatial ordering of query points: a counting sort on (scene, Morton code of a 16^3 cell).
 // Consecutive rows of the fused query kernel then touch neighbouring voxels, so the corner fetches
 // of the coarse feature levels (87 % of the gathered bytes) hit in L1 instead of going to L2.
-// The order inside a cell is irrelevant (every row is independent); only integer counters are used.
+// The sort is STABLE (rows of a cell keep their original order) and uses integer counters only, so the processing
+// order is reproducible run to run.
 #include "common.cuh"
 
 namespace svr {
@@ -28,12 +29,45 @@ __device__ __forceinline__ int point_key(const float *p) {
     return (int)(spread3(c[0]) << 2 | spread3(c[1]) << 1 | spread3(c[2]));
 }
 
-__global__ void sort_count_kernel(const float *__restrict__ pts, int N, int64_t total, int *__restrict__ key_of, int *__restrict__ count) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int key = (int)(i / N) * SORT_KEYS + point_key(pts + i * 3);
-    key_of[i] = key;
-    atomicAdd(count + key, 1);
+// STABLE counting sort (rows of one cell keep their original order), integer counters only: the processing order
+// -- and with it every fp32 reduction over rows downstream (split-K weight gradients, column sums, scatter) -- is the
+// same in every run.  A block owns SORT_BLOCK consecutive points of ONE scene:
+//   1. sort_count_kernel : key per point; rank of the point among the EARLIER points of its block with the same key
+//      (warps take turns in warp order, __match_any_sync inside a warp); per-(key, block) counts -> hist, per-key
+//      totals -> count (integer atomics: the sum is order-independent);
+//   2. sort_scan_kernel  : exclusive scan of count over (scene, key) -> start;
+//   3. sort_block_prefix_kernel : per key, exclusive prefix of hist over the scene's blocks;
+//   4. sort_fill_kernel  : perm[start[key] + hist[key][block] + rank] = point.
+constexpr int SORT_BLOCK = 1024;
+
+__global__ void __launch_bounds__(SORT_BLOCK) sort_count_kernel(const float *__restrict__ pts, int N, int nblk, int *__restrict__ key_rank,
+                                                                int *__restrict__ count, int *__restrict__ hist) {
+    __shared__ int cnt[SORT_KEYS];
+    const int scene = blockIdx.x / nblk, blk = blockIdx.x - scene * nblk;
+    const int local = blk * SORT_BLOCK + threadIdx.x;
+    const bool ok = local < N;
+    const int64_t i = (int64_t)scene * N + local;
+    for (int k = threadIdx.x; k < SORT_KEYS; k += SORT_BLOCK) cnt[k] = 0;
+    const int key = ok ? point_key(pts + i * 3) : -1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int before = __popc(peers & ((1u << lane) - 1));      // earlier lanes of this warp with the same key
+    int rank = 0;
+    __syncthreads();
+    for (int w = 0; w < SORT_BLOCK / 32; ++w) {                 // warps in order: deterministic ranks
+        if (w == warp && ok) {
+            rank = cnt[key] + before;
+            __syncwarp(peers);
+            if (before == 0) cnt[key] += __popc(peers);
+        }
+        __syncthreads();
+    }
+    if (ok) key_rank[i] = key | (rank << 12);                   // SORT_KEYS = 4096 keys, rank < 1024
+    for (int k = threadIdx.x; k < SORT_KEYS; k += SORT_BLOCK) {
+        const int c = cnt[k];
+        hist[((int64_t)scene * SORT_KEYS + k) * nblk + blk] = c;
+        if (c) atomicAdd(count + scene * SORT_KEYS + k, c);
+    }
 }
 
 // exclusive scan of `n` ints by ONE block of 1024 threads (n = B * 4096, a few thousand entries)
@@ -71,12 +105,27 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const int *__restrict__
     }
 }
 
-__global__ void sort_fill_kernel(const int *__restrict__ key_of, int64_t total, const int *__restrict__ start, int *__restrict__ cursor,
-                                 int *__restrict__ perm) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int key = key_of[i];
-    perm[start[key] + atomicAdd(cursor + key, 1)] = (int)i;
+// one thread per (scene, key): exclusive prefix of the key's per-block counts, in place
+__global__ void sort_block_prefix_kernel(int *__restrict__ hist, int nkeys, int nblk) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    int *h = hist + (int64_t)k * nblk;
+    int run = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int c = h[b];
+        h[b] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(SORT_BLOCK) sort_fill_kernel(const int *__restrict__ key_rank, int N, int nblk, const int *__restrict__ start,
+                                                               const int *__restrict__ hist, int *__restrict__ perm) {
+    const int scene = blockIdx.x / nblk, blk = blockIdx.x - scene * nblk;
+    const int local = blk * SORT_BLOCK + threadIdx.x;
+    if (local >= N) return;
+    const int64_t i = (int64_t)scene * N + local;
+    const int kr = key_rank[i], key = scene * SORT_KEYS + (kr & (SORT_KEYS - 1)), rank = kr >> 12;
+    perm[start[key] + hist[(int64_t)key * nblk + blk] + rank] = (int)i;
 }
 
 }  // namespace svr
@@ -85,8 +134,11 @@ using namespace svr;
 
 extern "C" {
 
+static inline int sort_nblk(int N) { return (N + SORT_BLOCK - 1) / SORT_BLOCK; }
+
 size_t svr_sort_points_workspace_bytes(int B, int N) {
-    return ((size_t)B * N + 3 * (size_t)B * SORT_KEYS) * sizeof(int) + 1024;
+    const size_t nkeys = (size_t)B * SORT_KEYS;
+    return ((((size_t)B * N + 63) / 64) * 64 + 2 * nkeys + nkeys * (size_t)sort_nblk(N)) * sizeof(int) + 1024;
 }
 
 int svr_sort_points(const float *points, int B, int N, int *perm, void *workspace, size_t workspace_bytes, void *stream) {
@@ -96,16 +148,17 @@ int svr_sort_points(const float *points, int B, int N, int *perm, void *workspac
     const int64_t total = (int64_t)B * N;
     if (total == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    const int nkeys = B * SORT_KEYS;
-    int *key_of = (int *)workspace;
-    int *count = key_of + (((size_t)total + 63) / 64) * 64;
-    int *cursor = count + nkeys;
-    int *start = cursor + nkeys;
-    SVR_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nkeys * sizeof(int), st));
-    const unsigned g = (unsigned)ceil_div<int64_t>(total, 256);
-    sort_count_kernel<<<g, 256, 0, st>>>(points, N, total, key_of, count);
+    const int nkeys = B * SORT_KEYS, nblk = sort_nblk(N);
+    SVR_REQUIRE((int64_t)B * nblk < ((int64_t)1 << 31), "sort_points: too many blocks");
+    int *key_rank = (int *)workspace;
+    int *count = key_rank + (((size_t)total + 63) / 64) * 64;
+    int *start = count + nkeys;
+    int *hist = start + nkeys;
+    SVR_CUDA(cudaMemsetAsync(count, 0, (size_t)nkeys * sizeof(int), st));
+    sort_count_kernel<<<(unsigned)(B * nblk), SORT_BLOCK, 0, st>>>(points, N, nblk, key_rank, count, hist);
     sort_scan_kernel<<<1, 1024, 0, st>>>(count, start, nkeys);
-    sort_fill_kernel<<<g, 256, 0, st>>>(key_of, total, start, cursor, perm);
+    sort_block_prefix_kernel<<<(unsigned)ceil_div(nkeys, 256), 256, 0, st>>>(hist, nkeys, nblk);
+    sort_fill_kernel<<<(unsigned)(B * nblk), SORT_BLOCK, 0, st>>>(key_rank, N, nblk, start, hist, perm);
     SVR_LAUNCH_CHECK();
     return 0;
 }

@@ -2,71 +2,132 @@
 
 The reference has no distributed code at all; the hot path shards by scene (training)
 and by point block (dense evaluation) with NO data-path collective.  The only exchange is the
-gradient all-reduce of the replicated weights (2 550 881 fp32 = 10.2 MB): two buckets, the decoder
-bucket is launched from a gradient hook as soon as the fused decoder backward has produced its
-gradients so that it overlaps the (torch/cuDNN) encoder backward.
+gradient all-reduce of the replicated weights (2 550 881 fp32 = 10.2 MB).
+
+``GradReducer`` keeps ONE persistent flat fp32 buffer per bucket.  Buckets follow the order in which the
+backward pass produces gradients (decoder first, then the encoder stages from the coarsest to ``conv_in``);
+each bucket is packed with one multi-tensor copy and its all-reduce (``ReduceOp.AVG`` on NCCL) is launched
+from the post-accumulate-grad hook of its last parameter, so that only the final ``conv_in`` bucket is
+exposed after ``backward``.  After the reduction ``p.grad`` is re-pointed at views of the flat buffer: no
+``torch.cat``, no copy back, no division kernel.
 
 BatchNorm: each rank normalises with its own shard's batch statistics (like DDP without SyncBN);
 parity of a DP step is therefore defined against a per-shard reference, see DESIGN.md."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
+# bucket = parameters whose name starts with one of the prefixes; listed in backward (gradient-ready) order
+DEFAULT_BUCKETS: Tuple[Tuple[str, ...], ...] = (
+    ("fc_",),
+    ("ifnet_feature_extractor.conv_3", "ifnet_feature_extractor.conv3", "ifnet_feature_extractor.conv_2", "ifnet_feature_extractor.conv2"),
+    ("ifnet_feature_extractor.conv_1", "ifnet_feature_extractor.conv1", "ifnet_feature_extractor.conv_0", "ifnet_feature_extractor.conv0"),
+)
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        self.index = {id(p): i for i, p in enumerate(params)}
+        n = sum(p.numel() for p in params)
+        dev, dt = params[0].device, params[0].dtype
+        self.flat = torch.zeros((n,), device=dev, dtype=dt)
+        self.views, off = [], 0
+        for p in params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.fired = set()
+        self.work = None
+        self.dirty = False      # a gradient changed after the bucket was packed (gradient accumulation): reduce again
+
 
 class GradReducer:
-    """Averages ``module``'s gradients over the process group after ``backward``."""
+    """Averages ``module``'s gradients over the process group.  Call ``allreduce()`` once after the last
+    ``backward()`` of a step.  ``weight`` is this rank's share of the global batch (default 1/world: equal
+    shards); with unequal shards (``shard_range`` with a remainder) pass ``n_local / n_global`` so that the result
+    is the gradient of the global-batch mean."""
 
-    def __init__(self, module: torch.nn.Module, early_prefixes: Sequence[str] = ("fc_",), group=None):
+    def __init__(self, module: torch.nn.Module, early_prefixes: Optional[Sequence[str]] = None, group=None,
+                 buckets: Optional[Sequence[Sequence[str]]] = None, weight: Optional[float] = None):
         self.group = group
         self.world = dist.get_world_size(group)
+        self.weight = weight
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
-        self.early = [p for n, p in named if n.startswith(tuple(early_prefixes))]
-        self.late = [p for n, p in named if not n.startswith(tuple(early_prefixes))]
-        self._pending = 0
-        self._early_work = None
-        self._early_flat: Optional[torch.Tensor] = None
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_early_grad) for p in self.early]
+        if buckets is None:
+            buckets = DEFAULT_BUCKETS if early_prefixes is None else (tuple(early_prefixes),)
+        groups: List[List[torch.nn.Parameter]] = [[] for _ in range(len(buckets) + 1)]
+        for n, p in named:
+            for bi, prefixes in enumerate(buckets):
+                if n.startswith(tuple(prefixes)):
+                    groups[bi].append(p)
+                    break
+            else:
+                groups[-1].append(p)     # everything else (conv_in, conv_in_bn, ...): last bucket
+        self.buckets = [_Bucket(g) for g in groups if g]
+        self._of: Dict[int, _Bucket] = {id(p): b for b in self.buckets for p in b.params}
+        self._avg = dist.get_backend(group) == "nccl" and weight is None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for b in self.buckets for p in b.params]
+        # kept for callers written against the two-bucket version
+        self.early = self.buckets[0].params
+        self.late = [p for b in self.buckets[1:] for p in b.params]
 
     # -- bucket helpers ---------------------------------------------------------------------------
-    @staticmethod
-    def _flatten(params: List[torch.Tensor]) -> torch.Tensor:
-        return torch.cat([p.grad.reshape(-1) for p in params])
+    def _launch(self, b: _Bucket):
+        grads = [p.grad for p in b.params]
+        if any(g is None for g in grads):      # parameters without a gradient contribute zeros (every rank still
+            b.flat.zero_()                     # runs the collective, so the replicas must agree on which they are)
+        dst_l, src_l = [], []
+        for p, g, v in zip(b.params, grads, b.views):
+            if g is not None and g.data_ptr() != v.data_ptr():
+                dst_l.append(v)
+                src_l.append(g.reshape(v.shape) if g.shape != v.shape else g)
+        if dst_l:
+            torch._foreach_copy_(dst_l, src_l)
+        if self.weight is not None:
+            b.flat.mul_(float(self.weight))
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+        b.dirty = False
 
-    @staticmethod
-    def _scatter_back(flat: torch.Tensor, params: List[torch.Tensor]):
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
-            off += n
-
-    def _on_early_grad(self, _param):
-        self._pending += 1
-        if self._pending == len(self.early):
-            self._early_flat = self._flatten(self.early)
-            self._early_work = dist.all_reduce(self._early_flat, group=self.group, async_op=True)
+    def _on_grad(self, param):
+        b = self._of[id(param)]
+        if id(param) in b.fired:          # second backward before allreduce(): the packed copy is stale
+            b.dirty = True
+            return
+        b.fired.add(id(param))
+        if len(b.fired) == len(b.params) and b.work is None:
+            # a gradient that already lives in the bucket buffer (zero_grad(set_to_none=False) after a previous step)
+            # would be reduced in place while a later micro-batch may still accumulate into it: leave such buckets
+            # to allreduce()
+            if not any(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(b.params, b.views)):
+                self._launch(b)
 
     # -- public -----------------------------------------------------------------------------------
     def allreduce(self):
-        """Call once after ``loss.backward()``: finishes the early bucket, reduces the late one."""
-        late_flat = None
-        if self.late and all(p.grad is not None for p in self.late):
-            late_flat = self._flatten(self.late)
-            late_work = dist.all_reduce(late_flat, group=self.group, async_op=True)
-        if self._early_work is None and self.early and all(p.grad is not None for p in self.early):
-            # hooks did not fire (e.g. gradients accumulated manually): reduce now
-            self._early_flat = self._flatten(self.early)
-            self._early_work = dist.all_reduce(self._early_flat, group=self.group, async_op=True)
-        if self._early_work is not None:
-            self._early_work.wait()
-            self._scatter_back(self._early_flat.div_(self.world), self.early)
-        if late_flat is not None:
-            late_work.wait()
-            self._scatter_back(late_flat.div_(self.world), self.late)
-        self._pending, self._early_work, self._early_flat = 0, None, None
+        """Finishes the buckets launched from the hooks, reduces the rest, and points every ``p.grad`` at its
+        (averaged) slice of the bucket buffer."""
+        for b in self.buckets:
+            if b.work is not None and b.dirty:
+                b.work.wait()
+                b.work = None
+            if b.work is None:
+                if all(p.grad is None for p in b.params):
+                    b.fired.clear()
+                    continue          # nothing produced a gradient for this bucket on any rank's replica of the graph
+                self._launch(b)
+        for b in self.buckets:
+            if b.work is None:
+                continue
+            b.work.wait()
+            if not self._avg and self.weight is None:
+                b.flat.div_(self.world)
+            for p, v in zip(b.params, b.views):
+                p.grad = v
+            b.work, b.dirty = None, False
+            b.fired.clear()
 
 
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:

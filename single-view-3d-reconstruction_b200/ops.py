@@ -5,6 +5,7 @@ an error."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import List, Optional, Sequence
 
 import torch
@@ -20,6 +21,41 @@ def _lib():
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_device_of(args):
+    """The one CUDA device all tensor arguments live on (None when there is no CUDA tensor: the callee then raises
+    its own "must be a CUDA tensor" error).  Tensors on different GPUs are an error, as they are for torch ops."""
+    dev = None
+    for a in args:
+        if isinstance(a, (list, tuple)):
+            d = _cuda_device_of(a)
+        elif torch.is_tensor(a) and a.is_cuda:
+            d = a.device
+        else:
+            continue
+        if d is None:
+            continue
+        if dev is not None and d != dev:
+            raise RuntimeError(f"svr_b200: tensor arguments live on different devices ({dev} and {d})")
+        dev = d
+    return dev
+
+
+def _entry(fn):
+    """Every call into the C ABI runs (a) with the tensors' device current, so that the stream handed to the library,
+    its per-device state (SM count, function attributes, scratch pool) and the allocations all belong to the device
+    that owns the data -- a module on cuda:1 works without torch.cuda.set_device, like torch's own ops; and (b) with
+    autocast disabled: the kernels take raw fp32 / bf16 pointers, so a tensor silently produced in half precision by
+    an autocast region (trainer_scene_net.py:230 passes precision=16 = native AMP) must never reach them."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = _cuda_device_of(args)
+        if dev is None:
+            return fn(*args, **kw)
+        with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -41,6 +77,7 @@ class _Unproject(torch.autograd.Function):
     """depth (B,H,W) -> points (B,H*W,3); projection.py:150-163,201-206 (+ :124-132 when normalise)."""
 
     @staticmethod
+    @_entry
     def forward(ctx, depth, f, cx, cy, scale, offset, dims, normalise):
         depth = _dev_f32(depth, "depthmap")
         B, H, W = depth.shape
@@ -51,6 +88,7 @@ class _Unproject(torch.autograd.Function):
         return pts
 
     @staticmethod
+    @_entry
     def backward(ctx, gpts):
         B, H, W, f, cx, cy, scale, dims, normalise = ctx.meta
         gpts = _dev_f32(gpts, "grad")
@@ -64,6 +102,7 @@ def unproject(depth, f, cx, cy, scale, offset, dims, normalise=False):
     return _Unproject.apply(depth, float(f), float(cx), float(cy), scale, offset, dims, normalise)
 
 
+@_entry
 def norm_grid_space_(pc: torch.Tensor, dims) -> torch.Tensor:
     """In-place projection.py:124-132 on a contiguous CUDA tensor (B,P,3)."""
     if not (pc.is_cuda and pc.dtype == torch.float32 and pc.is_contiguous()):
@@ -76,6 +115,7 @@ class _Voxelize(torch.autograd.Function):
     """project.pc_voxels (projection.py:39-80), bit-exact."""
 
     @staticmethod
+    @_entry
     def forward(ctx, points, dims, eps, tail_start):
         pts = _dev_f32(points, "points")
         B, N, _ = pts.shape
@@ -92,6 +132,7 @@ class _Voxelize(torch.autograd.Function):
         return grid
 
     @staticmethod
+    @_entry
     def backward(ctx, ggrid):
         pts, sat = ctx.saved_tensors
         B, N, dims, eps = ctx.meta
@@ -110,6 +151,7 @@ class _Blur(torch.autograd.Function):
     """project.voxels_smooth (projection.py:102-117): taps_w acts on the last axis, taps_d on the first."""
 
     @staticmethod
+    @_entry
     def forward(ctx, grid, taps_w, taps_h, taps_d):
         g = _dev_f32(grid, "voxels")
         tw, th, td = (_dev_f32(t.reshape(-1), "taps") for t in (taps_w, taps_h, taps_d))
@@ -126,6 +168,7 @@ class _Blur(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_entry
     def backward(ctx, gout):
         g, tw, th, td = ctx.saved_tensors
         gout = _dev_f32(gout, "grad")
@@ -152,11 +195,10 @@ class _MaxPool2CL(torch.autograd.Function):
     """nn.MaxPool3d(2) on a channels_last_3d activation without leaving NDHWC."""
 
     @staticmethod
+    @_entry
     def forward(ctx, x):
         B, Cc, D, H, W = x.shape
-        xp = x.permute(0, 2, 3, 4, 1)                      # NDHWC view of the channels-last tensor
-        if not xp.is_contiguous():
-            xp = xp.contiguous()
+        xp = _dev_f32(x.permute(0, 2, 3, 4, 1), "x")         # NDHWC view of the channels-last tensor (fp32, dense)
         out = torch.empty((B, D // 2, H // 2, W // 2, Cc), device=x.device, dtype=torch.float32)
         idx = torch.empty((out.numel() // 4,), device=x.device, dtype=torch.int32)
         _abi.check(_lib().svr_maxpool2_cl_fwd(xp.data_ptr(), B, D, H, W, Cc, out.data_ptr(), idx.data_ptr(), _stream()), "maxpool_fwd")
@@ -165,12 +207,11 @@ class _MaxPool2CL(torch.autograd.Function):
         return out.permute(0, 4, 1, 2, 3)                  # logical NCDHW, physically channels-last
 
     @staticmethod
+    @_entry
     def backward(ctx, gout):
         (idx,) = ctx.saved_tensors
         B, Cc, D, H, W = ctx.shape
-        g = gout.permute(0, 2, 3, 4, 1)
-        if not g.is_contiguous():
-            g = g.contiguous()
+        g = _dev_f32(gout.permute(0, 2, 3, 4, 1), "grad")
         gin = torch.empty((B, D, H, W, Cc), device=gout.device, dtype=torch.float32)
         _abi.check(_lib().svr_maxpool2_cl_bwd(g.data_ptr(), idx.data_ptr(), B, D, H, W, Cc, gin.data_ptr(), _stream()), "maxpool_bwd")
         return gin.permute(0, 4, 1, 2, 3)
@@ -180,6 +221,7 @@ class _Conv1ReLU(torch.autograd.Function):
     """relu(Conv3d(1 -> Co, 3, padding=1)(x)) with a channels-last output (first encoder layer)."""
 
     @staticmethod
+    @_entry
     def forward(ctx, x, weight, bias):
         x0 = _dev_f32(x, "x")
         B, _, D, H, W = x0.shape
@@ -194,13 +236,12 @@ class _Conv1ReLU(torch.autograd.Function):
         return y.permute(0, 4, 1, 2, 3)
 
     @staticmethod
+    @_entry
     def backward(ctx, gy):
         x0, y, w = ctx.saved_tensors
         B, _, D, H, W = x0.shape
         Co = w.shape[0]
-        g = gy.permute(0, 2, 3, 4, 1)
-        if not g.is_contiguous():
-            g = g.contiguous()
+        g = _dev_f32(gy.permute(0, 2, 3, 4, 1), "grad")
         gw = torch.empty((Co, 27), device=x0.device, dtype=torch.float32)
         gb = torch.empty((Co,), device=x0.device, dtype=torch.float32)
         gx = torch.empty_like(x0) if ctx.needs_input_grad[0] else None
@@ -224,6 +265,7 @@ class _Conv1ReLUBN(torch.autograd.Function):
     y_bf16 is the gather's bf16 NDHWC copy of y (non-differentiable, see ``pack_volume``)."""
 
     @staticmethod
+    @_entry
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, update_running, momentum, eps, with_pool,
                 keep_for_backward):
         x0 = _dev_f32(x, "x")
@@ -269,6 +311,7 @@ class _Conv1ReLUBN(torch.autograd.Function):
         return yv, y_bf16
 
     @staticmethod
+    @_entry
     def backward(ctx, gy, *rest):
         if not ctx.training:
             raise RuntimeError("svr_b200: the fused conv_in+ReLU+BN stage has no eval-mode backward; use the unfused modules")
@@ -328,6 +371,7 @@ class _ConvBf16Backward(torch.autograd.Function):
     at a relative gradient error of 3e-3 (bf16 rounding of the operands) instead of 3e-4 (TF32)."""
 
     @staticmethod
+    @_entry
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
         y = torch.nn.functional.conv3d(x, weight, bias, stride, padding, dilation, groups)
         cl = torch.channels_last_3d
@@ -336,6 +380,7 @@ class _ConvBf16Backward(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_entry
     def backward(ctx, gy):
         x_bf, weight = ctx.saved_tensors
         stride, padding, dilation, groups, has_bias = ctx.conf
@@ -354,9 +399,14 @@ class _ConvBiasReLU(torch.autograd.Function):
     bf16 (large layers) or fp32 operand of the convolution backward kernels in ONE pass."""
 
     @staticmethod
+    @_entry
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups, bf16_backward):
         cl = torch.channels_last_3d
+        if x.dtype != torch.float32 or weight.dtype != torch.float32:      # half-precision activations (AMP callers)
+            x, weight = x.float(), weight.float()
         y = torch.nn.functional.conv3d(x, weight, None, stride, padding, dilation, groups)
+        if y.dtype != torch.float32:
+            raise RuntimeError(f"svr_b200: conv3d returned {y.dtype}; the bias/ReLU kernel needs fp32")
         if not y.is_contiguous(memory_format=cl):
             y = y.contiguous(memory_format=cl)
         Co = y.shape[1]
@@ -368,6 +418,7 @@ class _ConvBiasReLU(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_entry
     def backward(ctx, gy):
         xs, weight, y = ctx.saved_tensors
         stride, padding, dilation, groups, has_bias, bf16_backward = ctx.conf
@@ -401,6 +452,7 @@ def conv3d_bias_relu(x, conv, bf16_backward):
     return _ConvBiasReLU.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, bf16_backward)
 
 
+@_entry
 def _to_bf16_channels_last(x):
     """bf16 copy of a channels-last fp32 activation through the vectorised convert kernel (torch's .to() falls back to
     a strided element-wise copy on permuted views: 2 TB/s)."""
@@ -409,6 +461,7 @@ def _to_bf16_channels_last(x):
     return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
 
 
+@_entry
 def _widen_bf16(t):
     """fp32 copy of a dense bf16 tensor with the same strides (vectorised; torch's .float() on a channels-last view is a
     strided element-wise copy)."""
@@ -447,6 +500,7 @@ class PyramidSpec:
         self.k = 7 * sum(self.channels)
 
 
+@_entry
 def pack_volume(v: torch.Tensor) -> torch.Tensor:
     """fp32 (B,C,D,H,W), any strides -> bf16 NDHWC contiguous (B,D,H,W,C)."""
     if not v.is_cuda:
@@ -497,6 +551,7 @@ class PackedDecoder:
         return self.t
 
 
+@_entry
 def swizzled_image(w):
     """(R, K) bf16 row-major matrix -> the K-chunked 128-byte-swizzled operand image the fused kernels stream."""
     img = torch.empty((w.numel() * 2,), device=w.device, dtype=torch.uint8)
@@ -533,6 +588,7 @@ USE_FUSED_BWD = True  # fused decoder backward-data chain (dz1, dz0, dfeat) when
 SORT_MIN_POINTS = 2048   # spatially sort the query points of a scene when it has at least this many
 
 
+@_entry
 def sort_points(pts: torch.Tensor) -> torch.Tensor:
     """(B,N,3) -> int32 (B*N,) processing order (scene-major, Morton order of 16^3 cells inside a scene)."""
     B, N, _ = pts.shape
@@ -581,6 +637,7 @@ def _decoder_struct(W, b0f, b1f, b2f, wof, bof):
     return dw
 
 
+@_entry
 def dense_eval(pyr, cache, x, vols, w0, b0, w1, b1, w2, b2, wo, bo, lattice, scenes=None, x_range=None):
     """sigmoid(decoder(sample(x, make_3d_grid lattice))) for whole scenes in ONE launch per scene
     (evaluate_network_on_grid, ifnet.py:215-229): the lattice points are generated inside the
@@ -613,6 +670,7 @@ class _Query(torch.autograd.Function):
     parameters.  Returns logits (B,N) fp32."""
 
     @staticmethod
+    @_entry
     def forward(ctx, pyr: PyramidSpec, cache: PackedDecoder, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
         pts = _dev_f32(points, "points")
         x0 = _dev_f32(x, "x")
@@ -651,6 +709,7 @@ class _Query(torch.autograd.Function):
         return logits.view(B, N)
 
     @staticmethod
+    @_entry
     def backward(ctx, glogits):
         pts, x0, feat, h0, h1, h2, wof, perm, *packed = ctx.saved_tensors
         perm = perm if ctx.has_perm else None
@@ -731,6 +790,7 @@ class _Gather(torch.autograd.Function):
     the kernel-order bf16 feature rows (B*N, KP)."""
 
     @staticmethod
+    @_entry
     def forward(ctx, pyr: PyramidSpec, points, x, *vols):
         pts = _dev_f32(points, "points")
         x0 = _dev_f32(x, "x")
@@ -743,6 +803,7 @@ class _Gather(torch.autograd.Function):
         return feat
 
     @staticmethod
+    @_entry
     def backward(ctx, gfeat):
         pts, x0, *packed = ctx.saved_tensors
         pyr = ctx.pyr

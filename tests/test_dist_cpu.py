@@ -47,6 +47,25 @@ def _worker(rank, world, port, out_dir):
         loss.backward()
         red.allreduce()
     torch.save({n: p.grad.clone() for n, p in net.named_parameters()}, Path(out_dir) / f"g{rank}.pt")
+    # gradient accumulation: two micro-batches (backward twice) before ONE allreduce -- the bucket launched from the
+    # hooks of the first backward is stale and must be reduced again
+    for keep_views in (False, True):
+        net.zero_grad(set_to_none=not keep_views)     # keep_views: p.grad stays a view of the bucket buffer
+        for half in (slice(0, 2), slice(2, 3)):
+            loss = ((net(mine["x"][half]) - mine["y"][half]) ** 2).sum(-1).sum() / 3.0
+            loss.backward()
+        red.allreduce()
+        torch.save({n: p.grad.clone() for n, p in net.named_parameters()}, Path(out_dir) / f"acc{int(keep_views)}_{rank}.pt")
+    # unequal shards: rank 0 takes 4 scenes, rank 1 takes 2; weights n_local / n_global
+    n_loc = 4 if rank == 0 else 2
+    sl = slice(0, 4) if rank == 0 else slice(4, 6)
+    red_w = svr_dist.GradReducer(net, weight=n_loc / 6.0)
+    for h in red._hooks:
+        h.remove()
+    net.zero_grad()
+    ((net(batch["x"][sl]) - batch["y"][sl]) ** 2).sum(-1).mean().backward()
+    red_w.allreduce()
+    torch.save({n: p.grad.clone() for n, p in net.named_parameters()}, Path(out_dir) / f"w{rank}.pt")
     dist.destroy_process_group()
 
 
@@ -62,6 +81,11 @@ def test_grad_reducer_matches_single_process(tmp_path):
     for n, p in net.named_parameters():
         assert torch.allclose(g0[n], g1[n])
         assert torch.allclose(g0[n], p.grad, rtol=1e-5, atol=1e-6), n
+        for tag in ("acc0", "acc1", "w"):
+            a0, a1 = torch.load(tmp_path / f"{tag}_{0}.pt" if tag != "w" else tmp_path / "w0.pt"), torch.load(
+                tmp_path / f"{tag}_{1}.pt" if tag != "w" else tmp_path / "w1.pt")
+            assert torch.allclose(a0[n], a1[n]), (tag, n)
+            assert torch.allclose(a0[n], p.grad, rtol=1e-5, atol=1e-6), (tag, n)
 
 
 def test_shard_range_covers_everything():

@@ -49,8 +49,3 @@ for fused, sortmin in ((False, 1 << 30), (True, 1 << 30), (True, 2048)):
         torch.cuda.synchronize()
     print("fused" if fused else "unfused", "sorted" if sortmin < 1 << 30 else "unsorted", "fwd ms (incl. volume + weight packing)", e0.elapsed_time(e1) / 10, flush=True)
 
-import ctypes
-from svr_b200 import _abi
-buf = (ctypes.c_uint64 * 12)()
-_abi.load()._cdll.svr_debug_fq_modes(buf, 1)
-print("tiles per (level, mode[cuda, tc]):", [(l, buf[2 * l], buf[2 * l + 1]) for l in range(6)])
