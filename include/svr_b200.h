@@ -161,6 +161,8 @@ int svr_sort_points(const float *points, int B, int N, int *perm, void *workspac
  *   flags: bit0 relu, bit1 store bf16 to c_bf16, bit2 store fp32 to c_f32,
  *          bit3 multiply by (mask[M,N] > 0) (bf16 mask, ld = ldc) -- relu backward,
  *          bit4 row-dot: out_dot[m] = sum_n epi(..)[m,n]*dot_w[n] + dot_b[0] (fc_out fused; N<=256)
+ *          bit5 accumulate: the product is added to the fp32 values already in c_f32 before bias/relu
+ *               (running sum of the hi/lo split products of the fp32 tier, see "fp32-accurate tier" below)
  * TN:  C[M,N] (+)= A[P,M]^T . B[P,N], A,B bf16 row-major (contraction over rows), fp32 out;
  *      workspace >= svr_gemm_tn_workspace_bytes(M,N,P).                                          */
 int svr_gemm_nt(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, const float *bias, int M, int N,
@@ -262,6 +264,31 @@ int svr_debug_fb_trace(void *buf);
 int svr_dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host,
                    const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, int sx, int sy, int sz,
                    int x_begin, int x_end, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32-accurate tier (`configure(precision=32)`): the reference's arithmetic for this path is fp32
+ * (model/ifnet.py:38-61 Conv1d in fp32, :155-199 F.grid_sample on fp32 volumes).  Volumes, features, hidden
+ * activations and gradients stay fp32 in HBM; the contractions run on the tensor cores as three bf16 GEMM passes
+ * over hi/lo splits of both operands (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, fp32 accumulation; svr_gemm_nt bit5,
+ * svr_gemm_tn accumulate).  csrc/precise.cu.
+ * ------------------------------------------------------------------------------------------- */
+/* x (n fp32, n % 8 == 0) -> hi = bf16(x), lo = bf16(x - hi)                                       */
+int svr_split_bf16(const float *x, int64_t n, uint16_t *hi, uint16_t *lo, void *stream);
+/* fc_0.weight (H0, C*7) in the reference's k = c*7+d order (ifnet.py:43-45) -> (H0, KP) fp32 in kernel order */
+int svr_pack_w0_f32(const float *w0, int H0, const svr_pyramid *pyr, float *w0p, void *stream);
+/* IFNetFeatureExtractor*.forward sampling (ifnet.py:156-197 / :93-118) on fp32 NDHWC volumes -> (B*N, KP) fp32 */
+int svr_gather_fwd_f32(const float *points, int B, int N, const float *x0, const float *const *vols_host,
+                       const svr_pyramid *pyr, float *feat, void *stream);
+/* its backward (ATen grid_sampler_3d_backward semantics) with fp32 d-features and fp32 trilinear weights;
+ * gx0 / gvols_host[l] / gpoints may be null (not needed)                                          */
+int svr_gather_bwd_f32(const float *points, int B, int N, const float *x0, const float *const *vols_host,
+                       const svr_pyramid *pyr, const float *dfeat, float *gx0, float *const *gvols_host,
+                       float *gpoints, void *stream);
+/* fc_out + relu(fc_2) backward in fp32: dz2 = dlogit (x) wout * [h2 > 0], gwout = sum dlogit*h2, gbout = sum dlogit */
+int svr_decoder_head_bwd_f32(const float *dlogit, const float *h2, const float *wout, int M, int Hd, float *dz2,
+                             float *gwout, float *gbout, void *stream);
+/* column sums of an fp32 (M, N) matrix (bias gradients), deterministic                            */
+int svr_colsum_f32(const float *a, int M, int N, int64_t lda, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -197,7 +197,13 @@ def gen_ifnet(ref_ifnet, net_res: int):
         for nm in ("fc_out", "fc_2", "fc_1", "fc_0"):
             out[f"{mode}_vjp_{nm}_w"] = getattr(net, nm).weight.grad.numpy()[:8].copy()
             out[f"{mode}_vjp_{nm}_b"] = getattr(net, nm).bias.grad.numpy().copy()
+            # FULL weight-gradient tensors (the 1e-3 tier is checked on every entry, not on a head)
+            out[f"{mode}_vjpfull_{nm}_w"] = getattr(net, nm).weight.grad.numpy().copy()
         out[f"{mode}_vjp_{first}_w"] = getattr(net.ifnet_feature_extractor, first).weight.grad.numpy().copy()
+        # every bias / BatchNorm gradient of the encoder: pins the gradient that reaches each sampled level
+        for pn, pv in net.ifnet_feature_extractor.named_parameters():
+            if pn.endswith(".bias") or "_bn." in pn:
+                out[f"{mode}_vjpenc_{pn}"] = pv.grad.numpy().copy()
         # the restatement must agree
         sd2 = {k: v.clone() for k, v in sd.items()}
         mine = R.ifnet_forward(sd2, x, pts, net_res, training=(mode == "train"))

@@ -87,6 +87,13 @@ _SIGS = {
     "svr_debug_fb_trace": (C.c_int, [vp]),
     "svr_dense_eval": (C.c_int, [C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), C.POINTER(DecoderWeights),
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    # fp32-accurate tier (csrc/precise.cu)
+    "svr_split_bf16": (C.c_int, [vp, C.c_int64, vp, vp, vp]),
+    "svr_pack_w0_f32": (C.c_int, [vp, C.c_int, C.POINTER(Pyramid), vp, vp]),
+    "svr_gather_fwd_f32": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), vp, vp]),
+    "svr_gather_bwd_f32": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), vp, vp, C.POINTER(vp), vp, vp]),
+    "svr_decoder_head_bwd_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "svr_colsum_f32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int64, vp, vp]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -98,6 +105,7 @@ KERNELS_PER_CALL = {
     "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
     "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 2, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
     "svr_decoder_head_bwd": 2, "svr_colsum_bf16": 2, "svr_query_fwd_fused": 1, "svr_dense_eval": 1, "svr_decoder_bwd_fused": 1, "svr_pack_decoder_image": 1, "svr_sort_points": 4, "svr_bias_relu_cl": 1, "svr_widen_bf16": 1, "svr_relu_bwd_cl": 2, "svr_conv1_relu_fwd": 1, "svr_conv1_relu_bwd": 2, "svr_conv1_relu_bn_stats": 2, "svr_conv1_relu_bn_apply": 1, "svr_conv1_relu_bn_bwd": 4, "svr_maxpool2_cl_fwd": 1, "svr_maxpool2_cl_bwd": 1,
+    "svr_split_bf16": 1, "svr_pack_w0_f32": 1, "svr_gather_fwd_f32": 1, "svr_gather_bwd_f32": 1, "svr_decoder_head_bwd_f32": 3, "svr_colsum_f32": 2,
 }
 
 

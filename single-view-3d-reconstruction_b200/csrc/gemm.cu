@@ -153,12 +153,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, (STAGES <= 2 ? 2 : 1)) gemm_nt_k
         const int row = m0 + warp * 32 + lane;
         const bool row_ok = row < p.M;
         const bool relu = p.flags & 1, st_bf = p.flags & 2, st_f = p.flags & 4, use_mask = p.flags & 8, dot = p.flags & 16;
+        const bool accum = p.flags & 32;   // C_f32 += A.B^T : the running sum of a split-operand (hi/lo) product, see precise.cu
         float dot_acc = 0.f;
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (n0 + c0 >= p.N) break;   // warp-uniform
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
             tmem_ld_wait();
+            if (accum && row_ok) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    int n = n0 + c0 + q * 4;
+                    if (n < p.N) {
+                        const float4 prev = *reinterpret_cast<const float4 *>(p.c_f32 + (int64_t)row * p.ldc + n);
+                        v[q * 4] = __float_as_uint(__uint_as_float(v[q * 4]) + prev.x);
+                        v[q * 4 + 1] = __float_as_uint(__uint_as_float(v[q * 4 + 1]) + prev.y);
+                        v[q * 4 + 2] = __float_as_uint(__uint_as_float(v[q * 4 + 2]) + prev.z);
+                        v[q * 4 + 3] = __float_as_uint(__uint_as_float(v[q * 4 + 3]) + prev.w);
+                    }
+                }
+            }
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -529,6 +543,7 @@ int svr_gemm_nt(const uint16_t *A, int64_t lda, const uint16_t *B, int64_t ldb, 
     SVR_REQUIRE(!(flags & 4) || (c_f32 && ldc % 4 == 0), "gemm_nt: fp32 output needs c_f32 and ldc %% 4 == 0");
     SVR_REQUIRE(!(flags & 8) || (mask && ldc % 8 == 0), "gemm_nt: mask needs a pointer and ldc %% 8 == 0");
     SVR_REQUIRE(!(flags & 16) || (dot_w && out_dot && N <= BN), "gemm_nt: row-dot needs dot_w/out_dot and N <= %d", BN);
+    SVR_REQUIRE(!(flags & 32) || (c_f32 && ldc % 4 == 0), "gemm_nt: accumulation needs the fp32 output");
     if (M == 0) return 0;
     GemmNT p{(const __nv_bfloat16 *)A, (const __nv_bfloat16 *)B, lda, ldb, ldc, bias, M, N, K, flags,
              (__nv_bfloat16 *)c_bf16, c_f32, (const __nv_bfloat16 *)mask, dot_w, dot_b, out_dot};

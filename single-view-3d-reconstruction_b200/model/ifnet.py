@@ -27,7 +27,7 @@ def _load_args():
             return _ref_arguments.parse_arguments()
     except (ImportError, SystemExit, Exception):
         pass
-    return types.SimpleNamespace(net_res=128, inf_res=1, num_points=2048, batch_size=16)
+    return types.SimpleNamespace(net_res=128, inf_res=1, num_points=2048, batch_size=16, precision=16)
 
 
 args = _load_args()
@@ -46,9 +46,38 @@ BF16_BACKWARD_MIN_VOXELS = 1 << 17
 
 
 def configure(**kw):
-    """Override module-level settings (net_res, inf_res, num_points, batch_size)."""
+    """Override module-level settings (net_res, inf_res, num_points, batch_size, precision).
+
+    ``precision`` mirrors the reference's ``--precision {32,16}`` flag (util/arguments.py:30): 16 (the default of this
+    package when the reference's parser is not importable) runs the query path with bf16 operands on the tensor cores
+    (logits within 1e-2 of the fp32 reference); 32 selects the fp32-accurate tier -- fp32 volumes / features /
+    activations, hi/lo-split tensor-core products, TF32 disabled in the cuDNN encoder (logits and gradients within 1e-3)."""
     for k, v in kw.items():
         setattr(args, k, v)
+    _apply_precision()
+
+
+def _precision() -> int:
+    return 32 if int(getattr(args, "precision", 16) or 16) == 32 else 16
+
+
+_TF32_BEFORE = None
+
+
+def _apply_precision():
+    """The cuDNN encoder (forward AND the backward autograd runs later) must not use TF32 in the fp32 tier: the switch
+    is global in torch, so it is flipped here and restored when the tier is left."""
+    global _TF32_BEFORE
+    if _precision() == 32:
+        if _TF32_BEFORE is None:
+            _TF32_BEFORE = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+    elif _TF32_BEFORE is not None:
+        torch.backends.cudnn.allow_tf32 = _TF32_BEFORE
+        _TF32_BEFORE = None
+
+
+_apply_precision()
 
 
 def _displacements(delta: float) -> torch.Tensor:
@@ -91,8 +120,8 @@ class _ExtractorBase(nn.Module):
     def _conv(self, conv, x):
         """conv(x); for the large channels-last layers (>= 2^20 input voxels) the backward kernels run on bf16
         operands (``args.bf16_conv_backward``, see ops._ConvBf16Backward) while the forward stays fp32/TF32."""
-        if (getattr(args, "bf16_conv_backward", True) and getattr(args, "channels_last", False) and x.is_cuda and x.dtype == torch.float32
-                and torch.is_grad_enabled() and conv.weight.requires_grad and conv.padding_mode == "zeros"
+        if (getattr(args, "bf16_conv_backward", True) and _precision() != 32 and getattr(args, "channels_last", False) and x.is_cuda
+                and x.dtype == torch.float32 and torch.is_grad_enabled() and conv.weight.requires_grad and conv.padding_mode == "zeros"
                 and x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= BF16_BACKWARD_MIN_VOXELS):
             return ops.conv3d_bf16_backward(x, conv)
         return conv(x)
@@ -105,7 +134,7 @@ class _ExtractorBase(nn.Module):
                 and conv.weight.dtype == torch.float32 and conv.padding_mode == "zeros" and co % 4 == 0 and 256 % (co // 4) == 0
                 and x.is_contiguous(memory_format=torch.channels_last_3d)):
             big = x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4] >= BF16_BACKWARD_MIN_VOXELS
-            return ops.conv3d_bias_relu(x, conv, bool(getattr(args, "bf16_conv_backward", True) and big))
+            return ops.conv3d_bias_relu(x, conv, bool(getattr(args, "bf16_conv_backward", True) and big and _precision() != 32))
         return self.actvn(self._conv(conv, x))
 
     def _first_stage(self, conv, bn, x):
@@ -256,11 +285,14 @@ class IFNet(nn.Module):
         """Hot path given precomputed volumes: stencil sampling + decoder -> logits (B,N)."""
         pyr = self.ifnet_feature_extractor.pyramid(x, vols)
         return ops.query(pyr, self._packed, points, x, self.fc_0.weight, self.fc_0.bias, self.fc_1.weight, self.fc_1.bias,
-                         self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, vols)
+                         self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, vols, precision=_precision())
+
+    def encode(self, x):
+        """The encoder's sampled volumes (in the fp32 tier cuDNN's TF32 convolutions are off, see ``_apply_precision``)."""
+        return self.ifnet_feature_extractor.encode(x)
 
     def forward(self, x, points):
-        vols = self.ifnet_feature_extractor.encode(x)
-        return self.query(x, vols, points)
+        return self.query(x, self.encode(x), points)
 
     def fused_available(self) -> bool:
         return self.fc_0.out_channels == 256 and self.fc_1.out_channels == 256 and self.fc_2.out_channels == 256
@@ -269,7 +301,7 @@ class IFNet(nn.Module):
     def evaluate_grid(self, x, lattice, scenes=None, x_range=None):
         """Dense occupancy of whole scenes on the (sx,sy,sz) inclusive lattice over [-0.5,0.5]^3:
         encoder once, then one fused launch per scene.  Returns a CUDA tensor (len(scenes),sx,sy,sz)."""
-        vols = self.ifnet_feature_extractor.encode(x)
+        vols = self.encode(x)
         pyr = self.ifnet_feature_extractor.pyramid(x, vols)
         return ops.dense_eval(pyr, self._packed, x, vols, self.fc_0.weight, self.fc_0.bias, self.fc_1.weight, self.fc_1.bias,
                               self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, lattice, scenes, x_range)
@@ -297,12 +329,12 @@ def evaluate_network_on_grid(network, x, resolution, res_increase=None):
     shape = tuple(int(res_increase * int(r)) for r in resolution)
     values = []
     with torch.no_grad():
-        if isinstance(network, IFNet) and not network.training and network.fused_available() and x.is_cuda:
+        if isinstance(network, IFNet) and not network.training and network.fused_available() and x.is_cuda and _precision() != 32:
             # one encoder pass + one fused launch: lattice generated on the fly (no 201 MB point tensor)
             return network.evaluate_grid(x, shape, scenes=[0])[0].cpu().numpy()
         if isinstance(network, IFNet) and not network.training:
-            vols = network.ifnet_feature_extractor.encode(x)
-            big = max(points_batch_size, 1 << 20)
+            vols = network.encode(x)
+            big = max(points_batch_size, 1 << 18 if _precision() == 32 else 1 << 20)
             try:
                 for ci, pi in enumerate(torch.split(pointsf, big)):
                     pi = pi.unsqueeze(0).to(x.device).expand(x.shape[0], -1, -1).contiguous()

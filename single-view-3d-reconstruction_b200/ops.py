@@ -777,11 +777,154 @@ class _Query(torch.autograd.Function):
         return (None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
 
 
-def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols):
+# =================================================================================================
+# fp32-accurate tier (csrc/precise.cu): fp32 tensors in HBM, hi/lo bf16 split products on the tensor cores
+# =================================================================================================
+ACCUM = 32
+
+
+def _split(x: torch.Tensor):
+    """fp32 (contiguous) -> (hi, lo) bf16 with x ~= hi + lo to 2^-17 relative."""
+    x = x.contiguous()
+    if x.numel() % 8:
+        raise RuntimeError("svr_b200: split needs a multiple of 8 elements")
+    hi, lo = torch.empty_like(x, dtype=_BF16), torch.empty_like(x, dtype=_BF16)
+    _abi.check(_lib().svr_split_bf16(x.data_ptr(), x.numel(), hi.data_ptr(), lo.data_ptr(), _stream()), "split_bf16")
+    return hi, lo
+
+
+def _mm_nt3(A, Bm, bias, M, N, K, out, flags=0, **kw):
+    """out (M,N) fp32 = epi(A . B^T + bias) with A = (hi, lo), B = (hi, lo): three tensor-core passes, fp32 running sum."""
+    _gemm_nt(A[0], Bm[0], None, M, N, K, ST_F32, c_f32=out, ldc=N)
+    _gemm_nt(A[1], Bm[0], None, M, N, K, ST_F32 | ACCUM, c_f32=out, ldc=N)
+    _gemm_nt(A[0], Bm[1], bias, M, N, K, ST_F32 | ACCUM | flags, c_f32=out, ldc=N, **kw)
+
+
+def _mm_tn3(A, Bm, M, N, P, out):
+    """out (M,N) fp32 = A^T . B with A (P,M) = (hi, lo), B (P,N) = (hi, lo) (contraction over the rows)."""
+    _gemm_tn(A[0], Bm[0], M, N, P, out, accumulate=False)
+    _gemm_tn(A[1], Bm[0], M, N, P, out, accumulate=True)
+    _gemm_tn(A[0], Bm[1], M, N, P, out, accumulate=True)
+
+
+def _colsum_f32(a: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((a.shape[1],), device=a.device, dtype=torch.float32)
+    _abi.check(_lib().svr_colsum_f32(a.data_ptr(), a.shape[0], a.shape[1], a.stride(0), out.data_ptr(), _stream()), "colsum_f32")
+    return out
+
+
+def _ndhwc_f32(v: torch.Tensor) -> torch.Tensor:
+    """(B,C,D,H,W) -> contiguous fp32 (B,D,H,W,C); a view when the encoder ran channels-last."""
+    if not v.is_cuda:
+        raise RuntimeError("svr_b200: feature volumes must be CUDA tensors; there is no CPU path")
+    return _dev_f32(v.permute(0, 2, 3, 4, 1), "volume")
+
+
+class _Query32(torch.autograd.Function):
+    """IFNet.forward given the encoder's volumes, fp32-accurate tier (ifnet.py:38-61,156-197 in fp32)."""
+
+    @staticmethod
+    @_entry
+    def forward(ctx, pyr: PyramidSpec, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
+        pts = _dev_f32(points, "points")
+        x0 = _dev_f32(x, "x")
+        B, N, _ = pts.shape
+        M, dev, KP = B * N, pts.device, pyr.kp
+        vf = [_ndhwc_f32(v.detach()) for v in vols]
+        h0n, h1n, h2n = w0.shape[0], w1.shape[0], w2.shape[0]
+        w0f = _dev_f32(w0.detach().reshape(h0n, -1), "weight")
+        if w0f.shape[1] != pyr.k:
+            raise RuntimeError(f"svr_b200: fc_0 expects {w0f.shape[1]} features, pyramid provides {pyr.k}")
+        w0p = torch.empty((h0n, KP), device=dev, dtype=torch.float32)
+        _abi.check(_lib().svr_pack_w0_f32(w0f.data_ptr(), h0n, C.byref(pyr.c), w0p.data_ptr(), _stream()), "pack_w0_f32")
+        w1f = _dev_f32(w1.detach().reshape(h1n, -1), "weight")
+        w2f = _dev_f32(w2.detach().reshape(h2n, -1), "weight")
+        b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
+        wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
+        feat = torch.empty((M, KP), device=dev, dtype=torch.float32)
+        vt = _abi.ptr_table([None] + [v.data_ptr() for v in vf])
+        _abi.check(_lib().svr_gather_fwd_f32(pts.data_ptr(), B, N, x0.data_ptr(), vt, C.byref(pyr.c), feat.data_ptr(), _stream()), "gather_fwd_f32")
+        F2 = _split(feat)
+        del feat
+        h0 = torch.empty((M, h0n), device=dev, dtype=torch.float32)
+        _mm_nt3(F2, _split(w0p), b0f, M, h0n, KP, h0, RELU)
+        H0 = _split(h0)
+        h1 = torch.empty((M, h1n), device=dev, dtype=torch.float32)
+        _mm_nt3(H0, _split(w1f), b1f, M, h1n, h0n, h1, RELU)
+        H1 = _split(h1)
+        h2 = torch.empty((M, h2n), device=dev, dtype=torch.float32)
+        logits = torch.empty((M,), device=dev, dtype=torch.float32)
+        _mm_nt3(H1, _split(w2f), b2f, M, h2n, h1n, h2, RELU | DOT, dot_w=wof, dot_b=bof, out_dot=logits)
+        if any(ctx.needs_input_grad):
+            ctx.pyr = pyr
+            ctx.vol_meta = [(v.shape, ctx.needs_input_grad[11 + i]) for i, v in enumerate(vols)]
+            ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[2], ctx.needs_input_grad[1]
+            ctx.shapes = (B, N, w0.shape, w1.shape, w2.shape, wo.shape)
+            ctx.save_for_backward(pts, x0, F2[0], F2[1], H0[0], H0[1], H1[0], H1[1], h2, w0p, w1f, w2f, wof, *vf)
+        return logits.view(B, N)
+
+    @staticmethod
+    @_entry
+    def backward(ctx, glogits):
+        pts, x0, fhi, flo, h0hi, h0lo, h1hi, h1lo, h2, w0p, w1f, w2f, wof, *vf = ctx.saved_tensors
+        pyr = ctx.pyr
+        B, N, s0, s1, s2, so = ctx.shapes
+        M, dev, KP = B * N, pts.device, pyr.kp
+        h0n, h1n, h2n = s0[0], s1[0], s2[0]
+        st = _stream()
+        dl = _dev_f32(glogits, "grad").reshape(-1)
+        dz2 = torch.empty((M, h2n), device=dev, dtype=torch.float32)
+        gwo = torch.empty((h2n,), device=dev, dtype=torch.float32)
+        gbo = torch.empty((1,), device=dev, dtype=torch.float32)
+        _abi.check(_lib().svr_decoder_head_bwd_f32(dl.data_ptr(), h2.data_ptr(), wof.data_ptr(), M, h2n, dz2.data_ptr(), gwo.data_ptr(),
+                                                   gbo.data_ptr(), st), "decoder_head_bwd_f32")
+        del h2
+        DZ2 = _split(dz2)
+        gw2 = torch.empty((h2n, h1n), device=dev, dtype=torch.float32)
+        _mm_tn3(DZ2, (h1hi, h1lo), h2n, h1n, M, gw2)
+        gb2 = _colsum_f32(dz2)
+        dz1 = torch.empty((M, h1n), device=dev, dtype=torch.float32)
+        _mm_nt3(DZ2, _split(w2f.t().contiguous()), None, M, h1n, h2n, dz1, MASK, mask=h1hi)     # (dz2 . W2) * [h1 > 0]
+        del dz2, DZ2
+        DZ1 = _split(dz1)
+        gw1 = torch.empty((h1n, h0n), device=dev, dtype=torch.float32)
+        _mm_tn3(DZ1, (h0hi, h0lo), h1n, h0n, M, gw1)
+        gb1 = _colsum_f32(dz1)
+        dz0 = torch.empty((M, h0n), device=dev, dtype=torch.float32)
+        _mm_nt3(DZ1, _split(w1f.t().contiguous()), None, M, h0n, h1n, dz0, MASK, mask=h0hi)
+        del dz1, DZ1
+        DZ0 = _split(dz0)
+        gw0p = torch.empty((h0n, KP), device=dev, dtype=torch.float32)
+        _mm_tn3(DZ0, (fhi, flo), h0n, KP, M, gw0p)
+        gw0 = torch.empty((h0n, pyr.k), device=dev, dtype=torch.float32)
+        _abi.check(_lib().svr_unpack_w0_grad(gw0p.data_ptr(), h0n, C.byref(pyr.c), gw0.data_ptr(), st), "unpack_w0_grad")
+        gb0 = _colsum_f32(dz0)
+        gvols_out: List[Optional[torch.Tensor]] = [None] * len(vf)
+        gx = gp = None
+        if any(m[1] for m in ctx.vol_meta) or ctx.x_needs or ctx.p_needs:
+            dfeat = torch.empty((M, KP), device=dev, dtype=torch.float32)
+            _mm_nt3(DZ0, _split(w0p.t().contiguous()), None, M, KP, h0n, dfeat)
+            gbufs = [torch.zeros((s[0], s[2], s[3], s[4], s[1]), device=dev, dtype=torch.float32) if needs else None
+                     for (s, needs) in ctx.vol_meta]
+            gx = torch.zeros_like(x0) if ctx.x_needs else None
+            gp = torch.zeros_like(pts) if ctx.p_needs else None
+            vt = _abi.ptr_table([None] + [v.data_ptr() for v in vf])
+            gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
+            _abi.check(_lib().svr_gather_bwd_f32(pts.data_ptr(), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
+                                                 _ptr(gp), st), "gather_bwd_f32")
+            gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
+        return (None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
+
+
+def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols, precision=16):
+    """``precision`` 16: bf16 operands on the tensor cores (logits within 1e-2 of the fp32 reference); 32: the fp32-accurate
+    tier (1e-3)."""
     if points.shape[0] * points.shape[1] == 0:          # empty query set: nothing to launch (ifnet.py:38-61 returns (B, 0))
         if not points.is_cuda:
             raise RuntimeError("svr_b200: `points` must be a CUDA tensor; there is no CPU path")
         return points.new_zeros((points.shape[0], points.shape[1]), dtype=torch.float32)
+    if int(precision) == 32:
+        return _Query32.apply(pyr, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
     return _Query.apply(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
 
 

@@ -60,3 +60,28 @@ def test_state_dict_keys_match_reference():
     import torch
     proj = svr_b200.project((139, 104, 112), [3, 3, 3], torch.tensor([1.5, 1.5, 1.5]))
     assert list(proj.state_dict().keys()) == ["sigma"]
+
+
+def test_get_intrinsic_parses_the_reference_file_format(tmp_path):
+    """projection.py:209-218 reads focal length, cx, cy from the first two rows of a text matrix in the format of the
+    reference's data/raw/overfit/00000/intrinsic.txt; without a file the package falls back to the same constants."""
+    import torch
+    import svr_b200
+    f = tmp_path / "intrinsic.txt"
+    f.write_text("[[300.25,   0.       , 161.5,  0.],\n[  0.       , 300.25, 118.25,  0.],\n"
+                 "[  0.       ,   0.       ,   1. ,  0.],\n[  0.       ,   0.       ,   0. ,  1.]]")
+    K = svr_b200.project.get_intrinsic(f)
+    want = torch.tensor([[300.25, 0, 161.5, 0], [0, 300.25, 118.25, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    assert K.dtype == torch.float32 and torch.equal(K, want)
+    K0 = svr_b200.project.get_intrinsic(tmp_path / "missing.txt")
+    assert abs(float(K0[0, 0]) - 277.1281435) < 1e-4 and float(K0[0, 2]) == 159.5 and float(K0[1, 2]) == 119.5
+
+
+def test_precision_switch_controls_tf32_and_restores_it():
+    import torch
+    import svr_b200
+    before = torch.backends.cudnn.allow_tf32
+    svr_b200.configure(precision=32)
+    assert torch.backends.cudnn.allow_tf32 is False
+    svr_b200.configure(precision=16)
+    assert torch.backends.cudnn.allow_tf32 == before

@@ -13,6 +13,18 @@ from oracle import ref_torch as R
 
 pytestmark = pytest.mark.gpu
 TOL_BF16 = 1e-2
+# bf16 tier, gradients against the fp32 reference (relative L2 per tensor): north_star gives no number; the bound is
+# set by ReLU decisions on bf16-rounded pre-activations (see tests/test_gpu_parity_r2.py); the fp32 tier meets 1e-3
+BF16_GRAD_TOL = 2.5e-1
+
+
+def _record(name, value):
+    import json
+    from pathlib import Path
+    d = Path(__file__).resolve().parent.parent / "gpurun_out"
+    if d.is_dir():
+        with open(d / "parity_r2.jsonl", "a") as f:
+            f.write(json.dumps({"name": name, "value": float(value)}) + "\n")
 
 
 def _rel(a, b):
@@ -110,10 +122,10 @@ def test_logits_and_gradients_vs_golden(golden, net_res, mode):
       (1) against a torch restatement of the same pipeline with the same bf16 rounding points:
           <= 3e-2 relative L2 (measured 1e-3 .. 1.4e-2; the residue is ReLU flips caused by 1-bf16-ulp
           differences between F.grid_sample and the gather) -- the parity bar for the backward kernels;
-      (2) against the unmodified fp32 reference (golden VJPs): cosine similarity >= 0.98.  An
-          element-wise bound is not meaningful there: ReLU decisions taken on bf16-rounded
-          pre-activations flip for ~0.3 % of the units, which alone is ~7 % relative L2 (the
-          reference's own AMP path has the same property)."""
+      (2) against the unmodified fp32 reference (golden VJPs, full tensors): relative L2 <= BF16_GRAD_TOL and cosine
+          similarity >= 0.98.  ReLU decisions taken on bf16-rounded pre-activations flip for ~0.3 % of the units,
+          which alone is several per cent relative L2 (the reference's own AMP path has the same property); the
+          fp32 tier (test_gpu_parity_r2.py) meets 1e-3 on every tensor."""
     g, sd = _case(golden, net_res)
     net = _net(net_res, sd)
     net.train(mode == "train")
@@ -135,11 +147,17 @@ def test_logits_and_gradients_vs_golden(golden, net_res, mode):
     for name, got in checks.items():
         c = _cos(got, g[f"{mode}_vjp_{name}"])
         assert c > 0.98, (name, c)
-    # (1) hot path on the same device volumes vs the bf16-pipeline restatement
+        e = _rel_l2(got, g[f"{mode}_vjp_{name}"])
+        _record(f"bf16/{net_res}/{mode}/{name}", e)
+        assert e < BF16_GRAD_TOL, (name, e)
+    for nm in ("fc_out", "fc_2", "fc_1", "fc_0"):      # full weight-gradient tensors
+        e = _rel_l2(getattr(net, nm).weight.grad, g[f"{mode}_vjpfull_{nm}_w"])
+        _record(f"bf16/{net_res}/{mode}/{nm}_w_full", e)
+        assert e < BF16_GRAD_TOL, (nm, e)
+    # (1) hot path on the same device volumes vs the bf16-pipeline restatement; in train mode the volumes come from a
+    # copy of the module so that the running statistics of `net` stay untouched
     with torch.no_grad():
-        vols = net.ifnet_feature_extractor.encode(x.detach()) if mode == "eval" else None
-    if vols is None:
-        return   # train-mode BN updates running stats on every encode; the eval cases cover (1)
+        vols = copy.deepcopy(net).ifnet_feature_extractor.encode(x.detach())
     net.zero_grad()
     x2 = x.detach().clone().requires_grad_(True)
     p2 = pts.detach().clone().requires_grad_(True)
