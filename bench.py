@@ -1,22 +1,27 @@
-"""Benchmark of the IF-Net implicit query hot path (BASELINE.json metric: IF-Net query-points/sec,
-fwd+bwd).
+"""Benchmark of the IF-Net implicit query hot path (BASELINE.json metric: IF-Net query-points/sec, fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config {1,2,3,5}]
 
-Workload (config.workload): BASELINE.json configs[1] -- IF-Net training step fwd+bwd, batch 4
-scenes x 50 000 query points, 128^3 occupancy grid per GPU (weak scaling: N GPUs = 4N scenes, which at
-N=8 is configs[3]'s 32 scenes).  A step = IFNet.forward (torch/cuDNN encoder + our gather/decoder
-kernels) + BCE loss + backward + DP gradient all-reduce (N>1) + Adam step.
+--config 2 (default; BASELINE.json configs[1], N GPUs = 4N scenes -- N=8 is configs[3]): IF-Net training step fwd+bwd,
+batch 4 scenes x 50 000 query points, 128^3 occupancy grid per GPU.  A step = IFNet.forward (cuDNN encoder + our
+first stage / glue + our gather/decoder kernels) + BCE loss + backward + DP gradient all-reduce (N>1) + Adam.
+--config 1 (configs[0]): one 256x256 depth map -> 128^3 grid -> IFNet.forward on 50 000 points, batch 1 (forward only).
+--config 3 (configs[2]): depth -> voxel projection sweep, batch 64 maps into 128^3 and 256^3 grids (depth maps / s).
+--config 5 (configs[4]): dense occupancy query on a 256^3 lattice, 8 scenes, sharded by (scene, x-slab) over the GPUs.
 
-  value : whole-job query-points/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the public module API with HOST (pinned) inputs; the H2D copies of the
-          voxel grids / points / labels and the D2H read of the loss are inside the timed region
-  roofline : dominant kernel of the step, timed live with CUDA events on the launching stream
-  cpu_baseline : the oracle port (oracle/ref_torch.py, torch CPU ops == the reference's arithmetic)
-          on the host cores, bounded sample, rank 0 / N=1 only
-  --impl reference : the reference's CPU implementation of the same step (the oracle port: the
-          reference is Python and does not exist on the GPU box), all host threads, bounded sample.
-"""
+Every line carries:
+  value     whole-job throughput with inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the public module API with HOST (pinned) inputs; H2D copies of the step's inputs
+            and the D2H read of its result are inside the timed region
+  roofline  the dominant kernel of the step (per KERNEL, timed live with CUDA events on the launching stream) against
+            the roofline that binds it, with SURVEY.md 8(d)'s algorithmic bytes / FLOPs; `rooflines` lists the other
+            hot-path kernels, `hot_path` = max(t_TC, t_HBM) / sum of the query-path kernels
+  gpu_reference  (N=1) the stock-torch CUDA implementation of the same step on the same GPU: the reference's own
+            arithmetic (oracle/ref_torch.py == model/ifnet.py's torch calls) run on ATen grid_sampler_3d{,_backward} +
+            cuDNN kernels -- the sm_100 bar to beat
+  cpu_baseline   (N=1) the same arithmetic on the host cores, bounded sample
+--impl reference: the reference's CPU implementation of the configuration (the oracle port: the reference is Python
+            and does not exist on the GPU box), all host threads, bounded sample."""
 from __future__ import annotations
 
 import argparse
@@ -35,8 +40,16 @@ SCENES_PER_GPU = 4
 POINTS = 50_000
 GRID = (128, 128, 128)
 DEPTH_HW = (256, 256)
-METRIC = "ifnet_query_points_per_sec_fwd_bwd"
 UNIT = "points/s"
+METRICS = {1: "ifnet_query_points_per_sec_fwd", 2: "ifnet_query_points_per_sec_fwd_bwd", 3: "depth_maps_per_sec_projection",
+           5: "ifnet_dense_eval_points_per_sec"}
+WORKLOADS = {
+    1: "IF-Net forward on one synthetic 256x256 depth map -> 128^3 voxel grid, 50k query points, batch 1 (BASELINE configs[0])",
+    2: "IF-Net training step fwd+bwd, batch 4 scenes x 50k query points, 128^3 grid per GPU (BASELINE configs[1]; N GPUs = 4N scenes, N=8 is configs[3])",
+    3: "depth->voxel projection sweep: batch 64 synthetic 256x256 depth maps into 128^3 and 256^3 occupancy grids (BASELINE configs[2])",
+    5: "dense occupancy query on a 256^3 evaluation grid (16.7M points per scene), batch 8 scenes sharded by (scene, x-slab) over the GPUs (BASELINE configs[4])",
+}
+FWD_FLOPS_PER_POINT = 2 * (2583 * 256 + 256 * 256 + 256 * 256 + 256)      # 1 585 152
 
 
 def _peaks():
@@ -120,26 +133,62 @@ def synthetic_inputs(n_scenes: int, seed: int, device):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# the reference's arithmetic through stock torch ops (oracle/ref_torch.py): CPU baseline / reference arm, and the
+# stock-torch CUDA arm on the same GPU
 # ------------------------------------------------------------------------------------------------
-def cpu_step_factory(n_points: int, seed: int = 0):
+def torch_step_factory(config: int, n_scenes: int, n_points: int, device, seed: int = 0):
+    """One step of `config` written with the reference's own torch calls; returns (step_fn, units_per_step)."""
     import torch
     from oracle import ref_torch as R
     g = torch.Generator().manual_seed(seed)
-    sd = R.synthetic_state_dict(0, 128)
-    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
-    x = (torch.rand((1, 1) + GRID, generator=g) < 0.03).float()
-    pts = torch.rand((1, n_points, 3), generator=g) - 0.5
-    occ = (torch.rand((1, n_points), generator=g) < 0.5).float()
+    dev = torch.device(device)
+    if config in (1, 2, 5):
+        sd = R.synthetic_state_dict(0, 128)
+        train = config == 2
+        params = {k: v.to(dev).requires_grad_(train and v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+        x = (torch.rand((n_scenes, 1) + GRID, generator=g) < 0.03).float().to(dev)
+        pts = (torch.rand((n_scenes, n_points, 3), generator=g) - 0.5).to(dev)
+        occ = (torch.rand((n_scenes, n_points), generator=g) < 0.5).float().to(dev)
+        if config == 2:
+            leaves = [p for p in params.values() if p.requires_grad]
+            opt = torch.optim.Adam(leaves, lr=1e-4)
 
-    def step():
-        for p in params.values():
-            p.grad = None
-        logits = R.ifnet_forward(params, x, pts, 128, training=True)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, occ, reduction="none").sum(-1).mean()
-        loss.backward()
-        return float(loss)
-    return step
+            def step():
+                opt.zero_grad(set_to_none=True)
+                logits = R.ifnet_forward(params, x, pts, 128, training=True)
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, occ, reduction="none").sum(-1).mean()
+                loss.backward()
+                opt.step()
+                return loss.detach()
+            return step, n_scenes * n_points
+
+        def step():      # configs 1 / 5: eval-mode forward (config 5: one chunk of evaluate_network_on_grid, encoder included)
+            with torch.no_grad():
+                return torch.sigmoid(R.ifnet_forward(params, x, pts, 128, training=False)).sum()
+        return step, n_scenes * n_points
+    if config == 3:
+        dims = torch.tensor(GRID)
+        depth = (torch.rand((n_scenes,) + DEPTH_HW, generator=g) * 5.0 + 0.5).to(dev)
+        K = R.intrinsic_matrix().to(dev)
+        sigma = torch.tensor([1.5, 1.5, 1.5], device=dev)
+
+        def step():
+            with torch.no_grad():
+                pc = R.norm_grid_space(R.depthmap_to_gridspace(depth, K, 1), dims)
+                return R.project_forward(pc, dims, sigma, [3, 3, 3]).sum()
+        return step, n_scenes
+    raise ValueError(config)
+
+
+def cpu_sample(config: int):
+    """(n_scenes, n_points, text) of the bounded CPU sample per configuration (about 10-30 s of CPU work)."""
+    if config == 2:
+        return 1, 25_000, "1 scene x 25000 points per step (128^3 grid, encoder + sampling + decoder fwd+bwd + Adam)"
+    if config == 1:
+        return 1, POINTS, "1 scene x 50000 points per step (128^3 grid, encoder + sampling + decoder forward)"
+    if config == 3:
+        return 2, 0, "2 depth maps of 256x256 per step into a 128^3 grid (unproject + pc_voxels + blur)"
+    return 1, 32_768, "one 32768-point chunk of evaluate_network_on_grid per step (the reference re-runs the encoder per chunk)"
 
 
 def run_reference(args):
@@ -147,48 +196,255 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    n_pts = 25_000
-    step = cpu_step_factory(n_pts)
-    for _ in range(max(args.warmup, 1)):
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core explicitly
+    n_sc, n_pts, sample = cpu_sample(args.config)
+    step, units = torch_step_factory(args.config, n_sc, n_pts, "cpu")
+    for _ in range(max(min(args.warmup, 2), 1)):
         step()
+    steps = max(1, args.steps)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    val = n_pts * args.steps / dt
-    sample = f"1 scene x {n_pts} points per step (128^3 grid, encoder + sampling + decoder fwd+bwd), torch CPU ops"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "IF-Net training step fwd+bwd, 128^3 grid, 50k query points/scene (BASELINE configs[1])",
-                       "scenes_per_gpu": SCENES_PER_GPU, "points_per_scene": POINTS, "grid": list(GRID)},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+    val = units * steps / dt
+    unit = "maps/s" if args.config == 3 else UNIT
+    line = {"impl": "reference", "metric": METRICS[args.config], "value": val, "unit": unit, "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(min(args.warmup, 2), 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args.config, 1),
+            "cpu_baseline": {"value": val, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": sample + ", torch CPU ops",
                              "host_cpus": os.cpu_count()},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------
-# our arm
-# ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def cpu_baseline(config: int):
     import torch
-    import torch.distributed as dist
+    n_sc, n_pts, sample = cpu_sample(config)
+    if config == 2:
+        n_pts = POINTS
+        sample = f"1 scene x {POINTS} points (of the 4-scene workload; scenes are independent), 1 timed step after 1 warm-up"
+    step, units = torch_step_factory(config, n_sc, n_pts, "cpu")
+    step()                      # warm-up (allocators, oneDNN primitives)
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return {"value": units / dt, "unit": "maps/s" if config == 3 else UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": os.cpu_count(), "sample": sample + ", oracle/ref_torch.py on torch CPU ops", "seconds": dt}
 
+
+def gpu_reference(config: int, dev, n_scenes: int):
+    """Stock torch CUDA kernels (ATen grid_sampler_3d / index_put / cuDNN, fp32 with torch's default TF32 convolutions) on
+    the SAME configuration and GPU: CUDA events, 2 warm-ups, 3 timed steps."""
+    import torch
+    try:
+        n_pts = POINTS if config != 5 else 32_768
+        if config == 3:
+            n_scenes = 8                                   # the reference's stack() needs 8x the grid: 64 maps would be 4.3 GB at 128^3
+        step, units = torch_step_factory(config, n_scenes, n_pts, dev)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        peak = torch.cuda.max_memory_allocated() / 1e9
+        out = {"value": units / ms * 1e3, "unit": "maps/s" if config == 3 else UNIT, "ms_per_step": ms, "dtype": "f32 (TF32 cuDNN convolutions, torch default)",
+               "kind": "stock torch CUDA: oracle/ref_torch.py (the reference's torch calls) on ATen/cuDNN sm_100 kernels, same GPU",
+               "sample": f"{n_scenes} scenes x {n_pts} points per step" if config != 3 else f"{n_scenes} depth maps per step (128^3)",
+               "peak_mem_gb": round(peak, 2)}
+        del step
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:      # e.g. out of memory: the arm is a reported baseline, never part of the product
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def config_block(config: int, world: int):
+    c = {"workload": WORKLOADS[config], "config_id": config, "l2": "inputs larger than L2 (volumes + features > 1 GB per step)",
+         "parallelism": f"dp{world}"}
+    if config in (1, 2):
+        c.update({"scenes_per_gpu": SCENES_PER_GPU if config == 2 else 1, "points_per_scene": POINTS, "grid": list(GRID)})
+    if config == 2:
+        c["step"] = "encoder(cuDNN convs + own first stage/glue)+gather+decoder fwd, BCE, bwd, allreduce(N>1), Adam"
+    if config == 3:
+        c.update({"maps": 64, "depth_hw": list(DEPTH_HW), "grids": [128, 256], "l2": "grids of 0.5 GB / 4.3 GB per step: larger than L2"})
+    if config == 5:
+        c.update({"scenes": 8, "lattice": [256, 256, 256], "grid": list(GRID), "l2": "67 MB output + 187 MB volumes per scene: larger than L2"})
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# rooflines (SURVEY.md 8(d) figures; DESIGN.md section 4)
+# ------------------------------------------------------------------------------------------------
+def _ncu_traffic(kernel_substr: str):
+    """dram read + write bytes per launch of a kernel from the newest committed `ncu --set full` summary (profiles/)."""
+    unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "Tbyte": 1e12}
+    for fname in ("r2_query_path.txt", "r2_projection.txt", "r1_query_path_v4.txt"):
+        f = ROOT / "profiles" / fname
+        if not f.exists():
+            continue
+        cur, rd, wr = False, None, None
+        for line in f.read_text().splitlines():
+            if line.startswith("== kernel"):
+                if cur and rd is not None and wr is not None:
+                    break
+                cur = kernel_substr in line
+            elif cur and line.startswith("dram__bytes_read.sum "):
+                v = line.split()
+                rd = float(v[-2]) * unit.get(v[-1], 1.0)
+            elif cur and line.startswith("dram__bytes_write.sum "):
+                v = line.split()
+                wr = float(v[-2]) * unit.get(v[-1], 1.0)
+        if rd is not None and wr is not None:
+            return rd + wr, f"profiles/{fname}"
+    return None, None
+
+
+def _roof(kernel, ms, calls, bound, work, peaks, ncu_name=None, note=None):
+    """One roofline record.  `work` = algorithmic FLOPs (tensor) or bytes (hbm) per launch."""
+    peak = peaks["bf16_tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"]
+    ach = work / (ms / max(calls, 1) * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+    traffic, src = _ncu_traffic(ncu_name) if ncu_name else (None, None)
+    r = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+         "frac": ach / peak, "traffic": traffic, "ms_per_step": ms, "launches_per_step": calls,
+         "algorithmic_" + ("flops" if bound == "tensor" else "bytes"): work,
+         "peak_source": peaks["source"] + (" (sustained bf16)" if bound == "tensor" else " (copy bandwidth)")}
+    if src:
+        r["traffic_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full ({src})"
+    if note:
+        r["note"] = note
+    return r
+
+
+def query_rooflines(kms, peaks, M, n_scenes, training=True):
+    """Per-KERNEL rooflines of the query path with SURVEY 8(d)'s figures: the (B,2583,N) feature tensor, dfeat and the saved
+    activations are NOT algorithmic bytes; FLOPs are 2583-wide."""
+    vol_elems = sum(c * (GRID[0] >> s) ** 3 for c, s in ((16, 0), (32, 1), (64, 2), (128, 3), (128, 4)))
+    lvl_elems = {1: 16 * GRID[0] ** 3, 2: 32 * (GRID[0] // 2) ** 3, 3: 64 * (GRID[0] // 4) ** 3, 4: 128 * (GRID[0] // 8) ** 3,
+                 5: 128 * (GRID[0] // 16) ** 3}
+    x_bytes = n_scenes * GRID[0] ** 3 * 4
+    vols_bf16 = n_scenes * vol_elems * 2
+    fwd_flops = M * FWD_FLOPS_PER_POINT
+    out = []
+
+    def add(key, *a, **k):
+        if key in kms:
+            calls, ms = kms[key]
+            out.append(_roof(key, ms, calls, *a, **k))
+
+    add("svr_query_fwd_fused", "tensor", fwd_flops, peaks, "fused_query_kernel",
+        f"fused gather + fc_0..fc_out; compulsory HBM bytes {vols_bf16 + x_bytes + 16 * M} (bf16 volumes + grid + 16 B/point)")
+    add("svr_dense_eval", "tensor", fwd_flops, peaks, "fused_query_kernel")
+    add("svr_decoder_bwd_fused", "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "fused_bwd_kernel", "dz1, dz0, dfeat in one kernel")
+    if "svr_gemm_tn" in kms:
+        calls, ms = kms["svr_gemm_tn"]
+        out.append(_roof("svr_gemm_tn", ms, 1, "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "gemm_tn_kernel",
+                         f"dW2 + dW1 + dW0 ({calls:g} launches + split-K reductions per step, timed together)"))
+    fine = n_scenes * (lvl_elems[1] + lvl_elems[2]) * 4 + 12 * M
+    coarse = n_scenes * (lvl_elems[3] + lvl_elems[4] + lvl_elems[5]) * 4 + 12 * M
+    add("svr_gather_bwd[direct]", "hbm", fine, peaks, "gather_bwd_kernel", "fp32 gradient volumes of levels 1-2 written once + points")
+    add("svr_gather_bwd[tensor-core]", "hbm", coarse, peaks, "scatter_tc_kernel", "fp32 gradient volumes of levels 3-5 written once + points")
+    add("svr_gather_bwd", "hbm", fine + coarse - 12 * M, peaks, "gather_bwd_kernel")
+    hot = None
+    if training and out:
+        t_tc = 3 * fwd_flops / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3
+        hbm_bytes = 2 * (vols_bf16 + x_bytes) + n_scenes * vol_elems * 4 + 32 * M          # fwd read + bwd re-read + fp32 dVolumes + points/logits
+        t_hbm = hbm_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+        total = sum(r["ms_per_step"] for r in out)
+        hot = {"t_tensor_ms": t_tc, "t_hbm_ms": t_hbm, "query_kernels_ms": total, "frac": max(t_tc, t_hbm) / total,
+               "note": "max(tensor-core bound of 3x forward FLOPs at the sustained bf16 peak, HBM bound of SURVEY 8(d)'s compulsory bytes with bf16 "
+                       "volumes) / sum of the query-path kernels (fused forward, fused decoder backward, weight-gradient GEMMs, scatters)"}
+    return out, hot
+
+
+# ------------------------------------------------------------------------------------------------
+# shared measurement plumbing
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from svr_b200 import _abi
+        self.abi = _abi
+        _abi.check(_abi.load().svr_device_info(None, None, None, None), "device_info")
+        self.args = args
+        self.clocks = ClockSampler(self.local)
+        if self.rank == 0:
+            self.clocks.start()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, sample_clocks=False):
+        """steps x fn between barrier + synchronize, CUDA events on the current stream, max over ranks -> total ms."""
+        torch = self.torch
+        self.barrier()
+        if sample_clocks:
+            self.clocks.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def kernel_pass(self, fn, steps):
+        """Per-kernel CUDA-event timing of `steps` further steps: name -> (calls per step, ms per step)."""
+        self.abi.PROFILE.reset(with_events=True)
+        self.barrier()
+        for i in range(steps):
+            fn(i)
+        self.barrier()
+        kms = {k: (c / steps, t / steps) for k, (c, t) in self.abi.PROFILE.kernel_ms().items()}
+        self.abi.PROFILE.reset(with_events=False)
+        return kms
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def base_line(ctx, config, value, ms_total, steps, unit=UNIT, scaling="weak", dtype="bf16"):
+    return {"metric": METRICS[config], "value": value, "unit": unit, "n_gpus": ctx.world, "steps": steps, "warmup": max(ctx.args.warmup, 3),
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": config_block(config, ctx.world)}
+
+
+def _kernel_table(kms):
+    return {k: {"calls": c, "ms": round(t, 4)} for k, (c, t) in sorted(kms.items(), key=lambda kv: -kv[1][1])}
+
+
+# ------------------------------------------------------------------------------------------------
+# config 2 (default): training step
+# ------------------------------------------------------------------------------------------------
+def run_config2(ctx):
+    torch, args = ctx.torch, ctx.args
     import svr_b200
-    from svr_b200 import _abi
     from svr_b200 import dist as svr_dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _abi.check(_abi.load().svr_device_info(None, None, None, None), "device_info")
-
-    svr_b200.configure(net_res=128, channels_last=os.environ.get("SVR_CHANNELS_LAST", "1") == "1")
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    svr_b200.configure(net_res=128, precision=16, channels_last=os.environ.get("SVR_CHANNELS_LAST", "1") == "1")
     torch.backends.cudnn.benchmark = os.environ.get("SVR_CUDNN_BENCHMARK", "1") == "1"   # reference: trainer_ifnet.py:64
     torch.manual_seed(0)
     net = svr_b200.IFNet().to(dev).train()
@@ -196,7 +452,6 @@ def run_ours(args):
     reducer = svr_dist.GradReducer(net) if world > 1 else None
     x, pts_h, occ_h = synthetic_inputs(SCENES_PER_GPU, 100 + rank, dev)
     pts, occ = pts_h.to(dev), occ_h.to(dev)
-    # host copies for the e2e leg
     x_pin, pts_pin, occ_pin = x.cpu().pin_memory(), pts_h.pin_memory(), occ_h.pin_memory()
     n_pts_step = SCENES_PER_GPU * POINTS
 
@@ -210,56 +465,30 @@ def run_ours(args):
         opt.step()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    # L2 hygiene: the step streams > 1 GB of volumes/features per iteration (inputs larger than the 126 MB L2)
     for _ in range(max(args.warmup, 3)):
         step(x, pts, occ)
     # ---------------- timed: device-resident inputs
-    _abi.PROFILE.reset(with_events=False)
-    barrier()
-    clocks.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.abi.PROFILE.reset(with_events=False)
     if args.profile_mode:
+        ctx.barrier()
         torch.cuda.profiler.start()      # ncu --profile-from-start off: only the timed steps are captured
-    e0.record()
-    for _ in range(args.steps):
-        step(x, pts, occ)
-    e1.record()
-    barrier()
+    ms = ctx.timed(lambda i: step(x, pts, occ), args.steps, sample_clocks=True)
     if args.profile_mode:
         torch.cuda.profiler.stop()
-    clk = clocks.stop() if rank == 0 else None
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = _abi.PROFILE.total_launches()
+    clk = ctx.clocks.stop() if rank == 0 else None
+    launches = ctx.abi.PROFILE.total_launches()
     value = world * n_pts_step * args.steps / (ms * 1e-3)
     if args.profile_mode:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "gpu_launches": launches,
+            print(json.dumps({"metric": METRICS[2], "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "gpu_launches": launches,
                               "profile_mode": True}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     # ---------------- timed: end to end from pinned host memory through the public API
     # Every step copies ITS inputs from pinned host memory (svr_b200.HostPrefetcher: the copy of step i+1 is issued on a
     # side stream while step i computes -- what a pinned DataLoader gives a trainer) and reads its loss back to the host
     # (4 bytes D2H into pinned memory).  The read is asynchronous with a lag of two steps, like a trainer that logs the
-    # loss without stalling the launch queue: the host consumes the loss of step i-2 while step i is being enqueued, and
-    # the last two are consumed before the timed region ends.
+    # loss without stalling the launch queue; the last two are consumed before the timed region ends.
     pf = svr_b200.HostPrefetcher(dev)
     host_batch = (x_pin, pts_pin, occ_pin)
     loss_pin = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -285,133 +514,240 @@ def run_ours(args):
         return losses
 
     e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e = ctx.timed(lambda i: e2e_loop(args.steps) if i == 0 else None, 1)
     e2e_value = world * n_pts_step * args.steps / (ms_e2e * 1e-3)
     h2d = x_pin.numel() * 4 + pts_pin.numel() * 4 + occ_pin.numel() * 4
 
     # ---------------- per-kernel timing (CUDA events on the launching stream, separate pass)
-    _abi.PROFILE.reset(with_events=True)
-    barrier()
     prof_steps = min(args.steps, 5)
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(prof_steps):
-        step(x, pts, occ)
+    kms = ctx.kernel_pass(lambda i: step(x, pts, occ), prof_steps)
     e1.record()
-    barrier()
+    torch.cuda.synchronize()
     step_ms_prof = e0.elapsed_time(e1) / prof_steps
-    kms = {k: (c / prof_steps, t / prof_steps) for k, (c, t) in _abi.PROFILE.kernel_ms().items()}
-    _abi.PROFILE.reset(with_events=False)
 
     if rank == 0:
         peaks = _peaks()
-        roof = roofline(kms, peaks, net)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic",
-                "config": {"workload": "IF-Net training step fwd+bwd, batch 4 scenes x 50k query points, 128^3 grid per GPU "
-                                       "(BASELINE configs[1]; N GPUs = 4N scenes, N=8 is configs[3])",
-                           "scenes_per_gpu": SCENES_PER_GPU, "points_per_scene": POINTS, "grid": list(GRID),
-                           "step": "encoder(torch/cuDNN)+gather+decoder fwd, BCE, bwd, allreduce(N>1), Adam",
-                           "l2": "inputs larger than L2 (volumes + features > 1 GB per step)", "parallelism": f"dp{world}"},
-                "clocks": clk, "gpu_launches": launches,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e / args.steps,
-                        "how": "public API (svr_b200.IFNet + HostPrefetcher): every step's inputs are copied from pinned host memory "
-                               "inside the timed region (the copy of step i+1 overlaps step i) and every step's loss is read back "
-                               "(async D2H, consumed with a lag of two steps, all consumed before the region ends)"},
-                "roofline": roof,
-                "kernels_ms_per_step": {k: {"calls": c, "ms": round(t, 4)} for k, (c, t) in sorted(kms.items(), key=lambda kv: -kv[1][1])},
-                "hot_path_ms_per_step": round(sum(t for _, t in kms.values()), 4), "step_ms_profiled": round(step_ms_prof, 4)}
+        roofs, hot = query_rooflines(kms, peaks, n_pts_step, SCENES_PER_GPU)
+        roofs.sort(key=lambda r: -r["ms_per_step"])
+        line = base_line(ctx, 2, value, ms, args.steps)
+        line.update({"clocks": clk, "gpu_launches": launches,
+                     "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                             "how": "public API (svr_b200.IFNet + HostPrefetcher): every step's inputs are copied from pinned host memory inside "
+                                    "the timed region (the copy of step i+1 overlaps step i) and every step's loss is read back (async D2H, "
+                                    "consumed with a lag of two steps, all consumed before the region ends)"},
+                     "roofline": roofs[0] if roofs else None, "rooflines": roofs[1:], "hot_path": hot,
+                     "kernels_ms_per_step": _kernel_table(kms), "own_kernels_ms_per_step": round(sum(t for _, t in kms.values()), 4),
+                     "step_ms_profiled": round(step_ms_prof, 4)})
+        if world == 1 and not args.no_gpu_reference:
+            del x_pin, pts_pin, occ_pin
+            torch.cuda.empty_cache()
+            line["gpu_reference"] = gpu_reference(2, dev, SCENES_PER_GPU)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(2)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def _ncu_traffic(profile_name: str, kernel_substr: str):
-    """dram read + write bytes per launch of a kernel from a committed `ncu --set full` summary (profiles/)."""
-    f = ROOT / "profiles" / profile_name
-    if not f.exists():
-        return None
-    unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
-    cur, rd, wr = False, None, None
-    for line in f.read_text().splitlines():
-        if line.startswith("== kernel"):
-            cur = kernel_substr in line
-        elif cur and line.startswith("dram__bytes_read.sum "):
-            v = line.split()
-            rd = float(v[-2]) * unit.get(v[-1], 1.0)
-        elif cur and line.startswith("dram__bytes_write.sum "):
-            v = line.split()
-            wr = float(v[-2]) * unit.get(v[-1], 1.0)
-    return None if rd is None or wr is None else rd + wr
+# ------------------------------------------------------------------------------------------------
+# config 1: depth map -> 128^3 grid -> IF-Net forward, batch 1
+# ------------------------------------------------------------------------------------------------
+def run_config1(ctx):
+    torch, args = ctx.torch, ctx.args
+    import svr_b200
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    svr_b200.configure(net_res=128, precision=16)
+    torch.manual_seed(0)
+    net = svr_b200.IFNet().to(dev).eval()
+    proj = svr_b200.project(GRID, [3, 3, 3], torch.tensor([1.5, 1.5, 1.5])).to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    depth_h = (torch.rand((1,) + DEPTH_HW, generator=g) * 5.0 + 0.5).pin_memory()
+    pts_h = (torch.rand((1, POINTS, 3), generator=g) - 0.5).pin_memory()
+    depth, pts = depth_h.to(dev), pts_h.to(dev)
+    out_pin = torch.empty((1, POINTS), dtype=torch.float32).pin_memory()
+
+    def step(d, p):
+        with torch.no_grad():
+            return net(proj(proj.depthmap_to_normed_points(d, 1)), p)
+
+    for _ in range(max(args.warmup, 3)):
+        step(depth, pts)
+    ctx.abi.PROFILE.reset(with_events=False)
+    ms = ctx.timed(lambda i: step(depth, pts), args.steps, sample_clocks=True)
+    clk = ctx.clocks.stop() if rank == 0 else None
+    launches = ctx.abi.PROFILE.total_launches()
+
+    def e2e_step(i):
+        out_pin.copy_(step(depth_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller holds the logits on the host after every call
+
+    e2e_step(0)
+    ms_e2e = ctx.timed(e2e_step, args.steps)
+    kms = ctx.kernel_pass(lambda i: step(depth, pts), min(args.steps, 5))
+    if rank == 0:
+        peaks = _peaks()
+        roofs, _ = query_rooflines(kms, peaks, POINTS, 1, training=False)
+        roofs.sort(key=lambda r: -r["ms_per_step"])
+        line = base_line(ctx, 1, world * POINTS * args.steps / (ms * 1e-3), ms, args.steps)
+        line.update({"clocks": clk, "gpu_launches": launches,
+                     "e2e": {"value": world * POINTS * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": depth_h.numel() * 4 + pts_h.numel() * 4,
+                             "d2h_bytes_per_step": POINTS * 4, "ms_per_step": ms_e2e / args.steps,
+                             "how": "project + IFNet.forward through the module API; depth map and points copied from pinned host memory and the "
+                                    "logits copied back to the host inside every timed step (synchronous per call)"},
+                     "roofline": roofs[0] if roofs else None, "rooflines": roofs[1:], "kernels_ms_per_step": _kernel_table(kms)})
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference(1, dev, 1)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(1)
+        print(json.dumps(line), flush=True)
 
 
-def roofline(kms, peaks, net):
-    """Roofline of the dominant hot-path kernel (largest share of the step among the IF-Net query kernels).
-    Algorithmic bytes / flops per launch are the figures of DESIGN.md section 4."""
-    hot = {k: v for k, v in kms.items() if k in ("svr_query_fwd_fused", "svr_gather_fwd", "svr_gather_bwd", "svr_gemm_nt", "svr_gemm_tn")}
-    if not hot:
-        return None
-    name, (calls, ms) = max(hot.items(), key=lambda kv: kv[1][1])
-    M = SCENES_PER_GPU * POINTS
-    kp = 2624
-    vol_elems = sum(c * (GRID[0] >> s) ** 3 for c, s in ((16, 0), (32, 1), (64, 2), (128, 3), (128, 4)))
-    x_bytes = SCENES_PER_GPU * GRID[0] ** 3 * 4
-    vols_bf16 = SCENES_PER_GPU * vol_elems * 2
-    fwd_flops = 2 * M * (kp * 256 + 2 * 256 * 256 + 256)
-    out = {"kernel": name, "ms_per_step": ms, "launches_per_step": calls, "traffic": None, "peak_source": peaks["source"]}
-    if name == "svr_query_fwd_fused":
-        # one launch: gather + fc_0..fc_out.  Tensor-core bound by the decoder FLOPs (DESIGN.md section 4);
-        # the achieved HBM rate on its compulsory bytes is reported next to it.
-        nbytes = vols_bf16 + x_bytes + M * 16 + M * kp * 2 + 3 * M * 256 * 2     # + saved features / activations (training)
-        ach = fwd_flops / (ms * 1e-3) / 1e12
-        out.update({"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "algorithmic_flops": fwd_flops, "algorithmic_bytes": nbytes,
-                    "hbm_achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                    "peak_source": peaks["source"] + " (sustained bf16)",
-                    "traffic": _ncu_traffic("r1_query_path_v4.txt", "fused_query_kernel"),
-                    "traffic_note": "dram read+write per launch, ncu --set full of the same training launch "
-                                    "(profiles/r1_query_path_v4.txt)"})
-    elif name in ("svr_gather_fwd", "svr_gather_bwd"):
-        # gather: volumes + grid in, feature rows out; scatter: d-feature rows in, fp32 gradient volumes written once
-        nbytes = (vols_bf16 + x_bytes + M * 12 + M * kp * 2) if name == "svr_gather_fwd" else (M * kp * 2 + 2 * vols_bf16 + M * 12)
-        ach = nbytes / (ms * 1e-3) / 1e9
-        out.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "algorithmic_bytes": nbytes})
-        if name == "svr_gather_bwd":       # one call = tensor-core scatter (coarse levels) + direct scatter (fine levels)
-            parts = [_ncu_traffic("r1_query_path_v4.txt", k) for k in ("scatter_tc_kernel", "gather_bwd_kernel")]
-            if all(v is not None for v in parts):
-                out["traffic"] = sum(parts)
-                out["traffic_note"] = ("dram read+write of scatter_tc_kernel + gather_bwd_kernel, ncu --set full of the same training step "
-                                       "(profiles/r1_query_path_v4.txt); above the algorithmic bytes because the fp32 gradient volumes are "
-                                       "read-modify-written by the L2 atomic units")
-    else:
-        flops = fwd_flops   # backward-data (dz1, dz0, dfeat) resp. weight-gradient (dW2, dW1, dW0) GEMMs: one forward's worth each
-        ach = flops / (ms * 1e-3) / 1e12
-        out.update({"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "algorithmic_flops": flops,
-                    "peak_source": peaks["source"] + " (sustained bf16)"})
-    return out
+# ------------------------------------------------------------------------------------------------
+# config 3: projection sweep
+# ------------------------------------------------------------------------------------------------
+def run_config3(ctx):
+    torch, args = ctx.torch, ctx.args
+    import svr_b200
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    B = 64                                                   # per GPU (depth maps are independent: weak scaling)
+    g = torch.Generator().manual_seed(100 + rank)
+    depth_h = (torch.rand((B,) + DEPTH_HW, generator=g) * 5.0 + 0.5).pin_memory()
+    depth = depth_h.to(dev)
+    peaks = _peaks()
+    sweep, clk, launches_total = [], None, 0
+    P = DEPTH_HW[0] * DEPTH_HW[1]
+    for S, scale in ((128, 1), (256, 0.5)):
+        dims = (S, S, S)
+        proj = svr_b200.project(dims, [3, 3, 3], torch.tensor([1.5, 1.5, 1.5])).to(dev)
+        chk = torch.zeros((), dtype=torch.float32).pin_memory()
+
+        def step(d):
+            with torch.no_grad():
+                return proj(proj.depthmap_to_normed_points(d, scale))
+
+        with torch.no_grad():
+            pts = proj.depthmap_to_normed_points(depth, scale)
+            for _ in range(max(args.warmup, 3)):
+                step(depth)
+            ctx.abi.PROFILE.reset(with_events=False)
+            ms = ctx.timed(lambda i: step(depth), args.steps, sample_clocks=(S == 128))
+            launches = ctx.abi.PROFILE.total_launches()
+            launches_total += launches
+            ms_vox = ctx.timed(lambda i: proj.pc_voxels(pts), args.steps)
+
+            def e2e_step(i):
+                out = step(depth_h.to(dev, non_blocking=True))
+                chk.copy_(out.sum(), non_blocking=True)   # the grid feeds IFNet on the device; the host reads a checksum
+                torch.cuda.current_stream().synchronize()
+
+            e2e_step(0)
+            ms_e2e = ctx.timed(e2e_step, args.steps)
+            kms = ctx.kernel_pass(lambda i: step(depth), min(args.steps, 5))
+        grid_bytes = B * S ** 3 * 4
+        roofs = []
+        for key, work, ncu, note in (("svr_voxelize_fwd", grid_bytes + B * P * 12, "vox_accumulate_kernel", "7 launches (bucket, rank, accumulate ...) timed together: points in + grid written once"),
+                                     ("svr_blur_fwd", 2 * grid_bytes, "blur_fused333_kernel", "grid read once + written once"),
+                                     ("svr_unproject_fwd", B * P * 16, "unproject", "depth in + points out")):
+            if key in kms:
+                roofs.append(_roof(key, kms[key][1], 1, "hbm", work, peaks, ncu, note))
+        roofs.sort(key=lambda r: -r["ms_per_step"])
+        if S == 128 and rank == 0:
+            clk = ctx.clocks.stop()
+        sweep.append({"grid": S, "scale_factor": scale, "maps_per_s": world * B * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                      "e2e_maps_per_s": world * B * args.steps / (ms_e2e * 1e-3), "pc_voxels_maps_per_s": world * B * args.steps / (ms_vox * 1e-3),
+                      "pc_voxels_ms": ms_vox / args.steps,
+                      "path_hbm_frac": (B * P * 4 + grid_bytes) / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "path_algorithmic_bytes": B * P * 4 + grid_bytes, "roofline": roofs[0] if roofs else None, "rooflines": roofs[1:],
+                      "kernels_ms_per_step": _kernel_table(kms), "gpu_launches": launches})
+        del proj, pts
+        torch.cuda.empty_cache()
+    if rank == 0:
+        s0 = sweep[0]
+        line = base_line(ctx, 3, s0["maps_per_s"], s0["ms_per_step"] * args.steps, args.steps, unit="maps/s", dtype="f32")
+        line.update({"clocks": clk, "gpu_launches": launches_total,
+                     "e2e": {"value": s0["e2e_maps_per_s"], "unit": "maps/s", "h2d_bytes_per_step": depth_h.numel() * 4, "d2h_bytes_per_step": 4,
+                             "how": "project.depthmap_to_normed_points + project.forward through the module API; the 64 depth maps are copied from "
+                                    "pinned host memory and a 4-byte checksum of the blurred grid is read back inside every timed step (the grid "
+                                    "itself is consumed on the device by IFNet in the reference's pipeline)"},
+                     "roofline": s0["roofline"], "sweep": sweep,
+                     "note": "value / roofline are the 128^3 leg (project.forward: unproject + voxelise + blur); the 256^3 leg is sweep[1]"})
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference(3, dev, 8)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(3)
+        print(json.dumps(line), flush=True)
 
 
-def cpu_baseline():
-    import torch
-    step = cpu_step_factory(POINTS)
-    step()                      # warm-up (allocators, oneDNN primitives)
-    t0 = time.perf_counter()
-    step()
-    dt = time.perf_counter() - t0
-    return {"value": POINTS / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": os.cpu_count(),
-            "sample": f"1 scene x {POINTS} points, 1 timed step after 1 warm-up (of the 4-scene workload; scenes are independent), "
-                      f"oracle/ref_torch.py on torch CPU ops", "seconds": dt}
+# ------------------------------------------------------------------------------------------------
+# config 5: dense 256^3 evaluation, 8 scenes sharded by (scene, x-slab)
+# ------------------------------------------------------------------------------------------------
+def run_config5(ctx):
+    torch, args = ctx.torch, ctx.args
+    import svr_b200
+    from svr_b200 import dist as svr_dist
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    svr_b200.configure(net_res=128, precision=16)
+    torch.manual_seed(0)
+    net = svr_b200.IFNet().to(dev).eval()
+    n_scenes, L, slab = 8, 256, 8
+    units = n_scenes * (L // slab)                               # (scene, 8-plane x-slab) units, contiguous block per rank
+    ub, ue = svr_dist.shard_range(units, rank, world)
+    per_scene = L // slab
+    mine = []                                                    # (scene, x_begin, x_end)
+    for sc in range(n_scenes):
+        b, e = max(ub, sc * per_scene), min(ue, (sc + 1) * per_scene)
+        if b < e:
+            mine.append((sc, (b - sc * per_scene) * slab, (e - sc * per_scene) * slab))
+    x_all, _, _ = synthetic_inputs(n_scenes, 7, dev)            # same scenes on every rank; a rank touches only its own
+    my_scenes = sorted({m[0] for m in mine})
+    x_pin = {sc: x_all[sc:sc + 1].cpu().pin_memory() for sc in my_scenes}
+    my_points = sum((e - b) * L * L for _, b, e in mine)
+
+    def step(_i=0, from_host=False, to_host=False):
+        outs = []
+        for sc, b, e in mine:
+            xs = x_pin[sc].to(dev, non_blocking=True) if from_host else x_all[sc:sc + 1]
+            o = net.evaluate_grid(xs, (L, L, L), scenes=[0], x_range=(b, e))[0, b:e]
+            outs.append(o.cpu() if to_host else o)
+        return outs
+
+    for _ in range(max(min(args.warmup, 3), 1)):
+        step()
+    steps = max(1, min(args.steps, 5))
+    ctx.abi.PROFILE.reset(with_events=False)
+    ms = ctx.timed(step, steps, sample_clocks=True)
+    clk = ctx.clocks.stop() if rank == 0 else None
+    launches = ctx.abi.PROFILE.total_launches()
+    ms_e2e = ctx.timed(lambda i: step(i, True, True), steps)
+    kms = ctx.kernel_pass(step, min(steps, 2))
+    total_points = n_scenes * L ** 3
+    if rank == 0:
+        peaks = _peaks()
+        roofs, _ = query_rooflines(kms, peaks, my_points, len(my_scenes), training=False)
+        roofs.sort(key=lambda r: -r["ms_per_step"])
+        line = base_line(ctx, 5, total_points * steps / (ms * 1e-3), ms, steps, scaling="strong")
+        line.update({"clocks": clk, "gpu_launches": launches,
+                     "e2e": {"value": total_points * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": len(my_scenes) * GRID[0] ** 3 * 4,
+                             "d2h_bytes_per_step": my_points * 4, "ms_per_step": ms_e2e / steps,
+                             "how": "IFNet.evaluate_grid (the engine behind evaluate_network_on_grid) per (scene, slab): the scene's voxel grid is "
+                                    "copied from pinned host memory and the occupancy slab copied back to the host inside every timed step"},
+                     "roofline": roofs[0] if roofs else None, "rooflines": roofs[1:], "kernels_ms_per_step": _kernel_table(kms),
+                     "ms_per_scene": ms / steps / max(len(mine), 1) * (L * L * L) / max(my_points / max(len(mine), 1), 1) if mine else None,
+                     "sharding": f"{units} (scene, {slab}-plane slab) units in contiguous blocks; rank 0 holds {len(mine)} blocks = {my_points} points"})
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference(5, dev, 1)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(5)
+        print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    try:
+        {1: run_config1, 2: run_config2, 3: run_config3, 5: run_config5}[args.config](ctx)
+    finally:
+        ctx.finish()
 
 
 def main():
@@ -420,7 +756,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5], help="BASELINE.json configuration (1-based; 4 = --config 2 with --gpus N)")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", dest="no_gpu_reference", action="store_true")
     ap.add_argument("--profile-mode", dest="profile_mode", action="store_true",
                     help="warm-up + timed device-resident steps only (the command profiled under ncu)")
     args = ap.parse_args()

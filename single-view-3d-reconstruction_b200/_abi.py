@@ -103,7 +103,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "svr_unproject_fwd": 1, "svr_unproject_bwd": 1, "svr_norm_grid_space": 1, "svr_voxelize_fwd": 7, "svr_voxelize_bwd": 1,
     "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
-    "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 2, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
+    "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 1, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
     "svr_decoder_head_bwd": 2, "svr_colsum_bf16": 2, "svr_query_fwd_fused": 1, "svr_dense_eval": 1, "svr_decoder_bwd_fused": 1, "svr_pack_decoder_image": 1, "svr_sort_points": 4, "svr_bias_relu_cl": 1, "svr_widen_bf16": 1, "svr_relu_bwd_cl": 2, "svr_conv1_relu_fwd": 1, "svr_conv1_relu_bwd": 2, "svr_conv1_relu_bn_stats": 2, "svr_conv1_relu_bn_apply": 1, "svr_conv1_relu_bn_bwd": 4, "svr_maxpool2_cl_fwd": 1, "svr_maxpool2_cl_bwd": 1,
     "svr_split_bf16": 1, "svr_pack_w0_f32": 1, "svr_gather_fwd_f32": 1, "svr_gather_bwd_f32": 1, "svr_decoder_head_bwd_f32": 3, "svr_colsum_f32": 2,
 }
@@ -117,6 +117,7 @@ class Profile:
         self.launches = {}
         self.calls = {}
         self.events = None          # None = off; dict name -> [(start, end)]
+        self.label = None           # one-shot name override for the next call (entry points used for several kernels)
 
     def reset(self, with_events=False):
         self.launches, self.calls = {}, {}
@@ -152,8 +153,9 @@ class _Lib:
 
         def call(*a):
             prof = PROFILE
-            prof.launches[name] = prof.launches.get(name, 0) + n_k
-            prof.calls[name] = prof.calls.get(name, 0) + 1
+            key, prof.label = (prof.label or name), None
+            prof.launches[key] = prof.launches.get(key, 0) + n_k
+            prof.calls[key] = prof.calls.get(key, 0) + 1
             if prof.events is None:
                 return fn(*a)
             import torch
@@ -161,7 +163,7 @@ class _Lib:
             e0.record()
             rc = fn(*a)
             e1.record()
-            prof.events.setdefault(name, []).append((e0, e1))
+            prof.events.setdefault(key, []).append((e0, e1))
             return rc
         return call
 

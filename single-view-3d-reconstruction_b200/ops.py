@@ -770,9 +770,20 @@ class _Query(torch.autograd.Function):
             if ctx.p_needs:
                 gp = torch.zeros_like(pts)
             vt = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
-            gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
-            _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
-                                             _ptr(gx), gt, _ptr(gp), st), "gather_bwd")
+            # With spatially sorted rows the library scatters the coarse levels (<= 40^3 voxels) on the tensor cores and
+            # the rest with direct vector reductions: two kernels.  They are issued as two calls (coarse-level table /
+            # everything else) so that each kernel is bracketed on its own by the profiler; the work is identical.
+            coarse = [perm is not None and g is not None and g.shape[1] * g.shape[2] * g.shape[3] <= 40 * 40 * 40 for g in gbufs]
+            fine_t = _abi.ptr_table([None] + [None if c else _ptr(g) for g, c in zip(gbufs, coarse)])
+            if gx is not None or gp is not None or any(g is not None and not c for g, c in zip(gbufs, coarse)):
+                _abi.PROFILE.label = "svr_gather_bwd[direct]"
+                _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
+                                                 _ptr(gx), fine_t, _ptr(gp), st), "gather_bwd")
+            if any(coarse):
+                coarse_t = _abi.ptr_table([None] + [_ptr(g) if c else None for g, c in zip(gbufs, coarse)])
+                _abi.PROFILE.label = "svr_gather_bwd[tensor-core]"
+                _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
+                                                 None, coarse_t, None, st), "gather_bwd")
             gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
         return (None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
 
