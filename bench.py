@@ -167,7 +167,7 @@ def torch_step_factory(config: int, n_scenes: int, n_points: int, device, seed: 
                 return torch.sigmoid(R.ifnet_forward(params, x, pts, 128, training=False)).sum()
         return step, n_scenes * n_points
     if config == 3:
-        dims = torch.tensor(GRID)
+        dims = torch.tensor(GRID).to(dev)
         depth = (torch.rand((n_scenes,) + DEPTH_HW, generator=g) * 5.0 + 0.5).to(dev)
         K = R.intrinsic_matrix().to(dev)
         sigma = torch.tensor([1.5, 1.5, 1.5], device=dev)
@@ -305,13 +305,14 @@ def _ncu_traffic(kernel_substr: str):
 
 
 def _roof(kernel, ms, calls, bound, work, peaks, ncu_name=None, note=None):
-    """One roofline record.  `work` = algorithmic FLOPs (tensor) or bytes (hbm) per launch."""
+    """One roofline record.  `work` = algorithmic FLOPs (tensor) or bytes (hbm) of ALL launches of the kernel in one step,
+    `ms` their summed duration: achieved = work / ms."""
     peak = peaks["bf16_tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"]
-    ach = work / (ms / max(calls, 1) * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+    ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
     traffic, src = _ncu_traffic(ncu_name) if ncu_name else (None, None)
     r = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
          "frac": ach / peak, "traffic": traffic, "ms_per_step": ms, "launches_per_step": calls,
-         "algorithmic_" + ("flops" if bound == "tensor" else "bytes"): work,
+         "algorithmic_" + ("flops" if bound == "tensor" else "bytes") + "_per_step": work,
          "peak_source": peaks["source"] + (" (sustained bf16)" if bound == "tensor" else " (copy bandwidth)")}
     if src:
         r["traffic_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full ({src})"
@@ -342,8 +343,8 @@ def query_rooflines(kms, peaks, M, n_scenes, training=True):
     add("svr_decoder_bwd_fused", "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "fused_bwd_kernel", "dz1, dz0, dfeat in one kernel")
     if "svr_gemm_tn" in kms:
         calls, ms = kms["svr_gemm_tn"]
-        out.append(_roof("svr_gemm_tn", ms, 1, "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "gemm_tn_kernel",
-                         f"dW2 + dW1 + dW0 ({calls:g} launches + split-K reductions per step, timed together)"))
+        out.append(_roof("svr_gemm_tn", ms, calls, "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "gemm_tn_kernel",
+                         "dW2 + dW1 + dW0 (three GEMM launches + their split-K reductions per step, timed together)"))
     fine = n_scenes * (lvl_elems[1] + lvl_elems[2]) * 4 + 12 * M
     coarse = n_scenes * (lvl_elems[3] + lvl_elems[4] + lvl_elems[5]) * 4 + 12 * M
     add("svr_gather_bwd[direct]", "hbm", fine, peaks, "gather_bwd_kernel", "fp32 gradient volumes of levels 1-2 written once + points")

@@ -109,6 +109,10 @@ int svr_feature_kp(const svr_pyramid *pyr_host);
 /* fp32 volume with arbitrary element strides (B,C,D,H,W) -> bf16 NDHWC contiguous.              */
 int svr_pack_volume(const float *src, int B, int C, int D, int H, int W, int64_t sB, int64_t sC,
                     int64_t sD, int64_t sH, int64_t sW, uint16_t *dst, void *stream);
+/* same source -> bf16 (B, D+2, H+2, W+2, C) with a one-voxel zero halo (C % 8 == 0): the zero padding of
+ * F.grid_sample (ifnet.py:162-193, padding_mode='zeros') materialised, for the fused kernel's wide path */
+int svr_pack_volume_halo(const float *src, int B, int C, int D, int H, int W, int64_t sB, int64_t sC,
+                         int64_t sD, int64_t sH, int64_t sW, uint16_t *dst, void *stream);
 /* fp32 NDHWC contiguous gradient -> accumulate (+=) into fp32 tensor with arbitrary strides.    */
 int svr_unpack_volume_grad(const float *src_ndhwc, int B, int C, int D, int H, int W, int64_t sB,
                            int64_t sC, int64_t sD, int64_t sH, int64_t sW, float *dst, int accumulate,
@@ -200,10 +204,15 @@ typedef struct svr_decoder_weights {
 /* bf16 row-major (R, K) -> K/64 chunks of (R x 128 B) in the 128B-swizzled K-major UMMA layout   */
 int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *image, void *stream);
 
+/* debug only: SM-clock timeline of block 0 (4 roles x 1024 x (tag, clock) int64, device buffer; null = off) */
+int svr_debug_fq_trace(void *buf);
+
+/* halo_vols_host (nullable table, nullable entries): svr_pack_volume_halo copies of the levels with
+ * C % 64 == 0; the trailing run of such levels is sampled through the kernel's bounds-check-free wide path  */
 int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, const float *x0,
-                        const uint16_t *const *vols_host, const svr_pyramid *pyr_host,
-                        const svr_decoder_weights *w_host, float *logits, uint16_t *save_h,
-                        uint16_t *save_feat, int apply_sigmoid, void *stream);
+                        const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host,
+                        const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, float *logits,
+                        uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream);
 
 /* First stage of the 128-net fused: y = BatchNorm3d(relu(Conv3d(1 -> 16, 3, padding 1)(x))), channels-last y
  * (model/ifnet.py:126,137,164 `net = self.actvn(self.conv_in(x)); net = self.conv_in_bn(net)`).  The pre-BN
@@ -262,8 +271,9 @@ int svr_debug_fb_trace(void *buf);
  * z-slab [x_begin, x_end) of the FIRST lattice axis, generating the points on the fly; out is the
  * (sx,sy,sz) fp32 grid of ONE scene (only the slab is written).                                  */
 int svr_dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host,
-                   const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, int sx, int sy, int sz,
-                   int x_begin, int x_end, float *out, void *stream);
+                   const uint16_t *const *halo_vols_host, const svr_pyramid *pyr_host,
+                   const svr_decoder_weights *w_host, int sx, int sy, int sz, int x_begin, int x_end, float *out,
+                   void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * fp32-accurate tier (`configure(precision=32)`): the reference's arithmetic for this path is fp32

@@ -49,6 +49,8 @@ _SIGS = {
     "svr_feature_kp": (C.c_int, [C.POINTER(Pyramid)]),
     "svr_pack_volume": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_int64, C.c_int64, vp, vp]),
+    "svr_pack_volume_halo": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_int64, C.c_int64, vp, vp]),
     "svr_unpack_volume_grad": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int64, vp, C.c_int, vp]),
     "svr_pack_w0": (C.c_int, [vp, C.c_int, C.POINTER(Pyramid), vp, vp, vp]),
@@ -71,8 +73,8 @@ _SIGS = {
     "svr_decoder_head_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "svr_colsum_bf16": (C.c_int, [vp, C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp]),
     "svr_pack_decoder_image": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
-    "svr_query_fwd_fused": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), C.POINTER(DecoderWeights),
-                                      vp, vp, vp, C.c_int, vp]),
+    "svr_query_fwd_fused": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Pyramid),
+                                      C.POINTER(DecoderWeights), vp, vp, vp, C.c_int, vp]),
     "svr_conv1_bn_workspace_bytes": (C.c_size_t, []),
     "svr_conv1_relu_bn_stats": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp,
                                           C.c_size_t, vp]),
@@ -85,7 +87,8 @@ _SIGS = {
     "svr_relu_bwd_cl": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, C.c_size_t, vp]),
     "svr_decoder_bwd_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp]),
     "svr_debug_fb_trace": (C.c_int, [vp]),
-    "svr_dense_eval": (C.c_int, [C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), C.POINTER(DecoderWeights),
+    "svr_debug_fq_trace": (C.c_int, [vp]),
+    "svr_dense_eval": (C.c_int, [C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Pyramid), C.POINTER(DecoderWeights),
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     # fp32-accurate tier (csrc/precise.cu)
     "svr_split_bf16": (C.c_int, [vp, C.c_int64, vp, vp, vp]),
@@ -102,7 +105,7 @@ _lib = None
 # kernels launched per entry point (memsets are not kernels of ours and are not counted)
 KERNELS_PER_CALL = {
     "svr_unproject_fwd": 1, "svr_unproject_bwd": 1, "svr_norm_grid_space": 1, "svr_voxelize_fwd": 7, "svr_voxelize_bwd": 1,
-    "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
+    "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_pack_volume_halo": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
     "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 1, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
     "svr_decoder_head_bwd": 2, "svr_colsum_bf16": 2, "svr_query_fwd_fused": 1, "svr_dense_eval": 1, "svr_decoder_bwd_fused": 1, "svr_pack_decoder_image": 1, "svr_sort_points": 4, "svr_bias_relu_cl": 1, "svr_widen_bf16": 1, "svr_relu_bwd_cl": 2, "svr_conv1_relu_fwd": 1, "svr_conv1_relu_bwd": 2, "svr_conv1_relu_bn_stats": 2, "svr_conv1_relu_bn_apply": 1, "svr_conv1_relu_bn_bwd": 4, "svr_maxpool2_cl_fwd": 1, "svr_maxpool2_cl_bwd": 1,
     "svr_split_bf16": 1, "svr_pack_w0_f32": 1, "svr_gather_fwd_f32": 1, "svr_gather_bwd_f32": 1, "svr_decoder_head_bwd_f32": 3, "svr_colsum_f32": 2,

@@ -5,17 +5,23 @@
 // (evaluate_network_on_grid, ifnet.py:215-229) by generating the make_3d_grid lattice on the fly in
 // brick order.
 //
-// One CTA per SM, 128 query points per tile, 448 threads:
+// One CTA per SM, 128 query points per tile, 704 threads:
 //   warps 0-3   epilogue: TMEM -> registers -> (+bias, ReLU, bf16) -> H tile in smem / logits
 //   warp  4     weight loader: cp.async.bulk (UBLKCP) of pre-swizzled 32 KB weight chunks
 //   warp  5     single-thread tcgen05.mma issue
-//   warps 6-13  gather producers: 8 corners x 16 B channel-last loads per (point, unit), trilinear
-//               blend in fp32, bf16 pack, st.shared into the swizzled A stage
+//   warps 6-21  gather producers: 8 corners x 16 B channel-last loads per (point, unit), trilinear
+//               blend in fp32, bf16 pack, st.shared into the swizzled A stage.
+//               Two code paths: the generic one (any level, bounds-checked corners) and the WIDE path for levels
+//               with C % 64 == 0 whose volumes come with a one-voxel zero halo (svr_pack_volume_halo): a sample
+//               descriptor (corner base pointer + 8 trilinear weights, no bounds logic: the halo supplies the
+//               zeros of grid_sample's zero padding) is computed once per (row, stencil point) and reused for all
+//               the level's channel groups of the thread (C/64 consecutive K chunks).
 // TMEM: acc0 = columns [0,256) (fc_0), acc1 = [256,512) (fc_1 and fc_2).  Issue order per tile i:
 //   F1(i) | F0(i+1) | F2(i)   so that the long fc_0 of the next tile overlaps this tile's epilogues.
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace svr {
 using namespace tc;
@@ -29,7 +35,20 @@ constexpr int FQ_H_BYTES = FQ_TILE * FQ_HID * 2; // 64 KB: 4 K-chunks of 16 KB
 constexpr int FQ_EPI_WARPS = 4;
 constexpr int fq_threads(int gather_warps) { return (FQ_EPI_WARPS + 2 + gather_warps) * 32; }   // 448 for 8 gather warps
 constexpr int FQ_UTAB = 512;                     // unit table entries (KP <= 4096)
-constexpr int FQ_SMEM = 1024 + FQ_NA * FQ_A_BYTES + FQ_NB * FQ_B_BYTES + FQ_H_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4;
+constexpr int FQ_WGEO_BYTES = 512;               // per-level geometry of the wide path
+constexpr int FQ_SMEM = 1024 + FQ_NA * FQ_A_BYTES + FQ_NB * FQ_B_BYTES + FQ_H_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4 + FQ_WGEO_BYTES;
+
+// geometry of one WIDE level (C % 64 == 0) sampled from its halo'd copy (B, D+2, H+2, W+2, C), see the header comment
+struct WideGeo {
+    float fw, fh, fd;              // unpadded sizes
+    int C, sy, sz;                 // element strides of a y / z step in the halo'd volume: (W+2)*C, (H+2)*(W+2)*C
+    int cpd;                       // K chunks per stencil point (C / 64)
+    int chunk0;                    // first K chunk of the level
+    int spec;                      // compile-time specialisation id of (C, sy, sz); 0 = runtime strides
+    long long scene;               // halo'd elements per scene
+    const __nv_bfloat16 *base;     // halo'd volume
+};
+static_assert(sizeof(WideGeo) * SVR_MAX_LEVELS <= FQ_WGEO_BYTES, "wide geometry table");
 
 struct FqVols {
     const __nv_bfloat16 *v[SVR_MAX_LEVELS];
@@ -45,6 +64,8 @@ struct FqParams {
     int lat_scene, sx, sy, sz, x_begin, bx, by, bz;   // bricks per axis over [x_begin, x_end) x sy x sz
     const float *x0;
     FqVols vols;
+    FqVols halo;                // optional halo'd copies of the wide levels (null entries: generic path)
+    int wide_level0;            // first level taken by the wide path (== P.n_levels: none); every level from here on is wide
     Pyr P;
     const uint8_t *w0_img, *w1_img, *w2_img;   // pre-swizzled chunk images (svr_pack_decoder_images)
     const float *b0, *b1, *b2, *wout, *bout;
@@ -52,7 +73,18 @@ struct FqParams {
     __nv_bfloat16 *save_h;      // optional (3, total, 256)
     __nv_bfloat16 *save_feat;   // optional (total, KP)
     int apply_sigmoid;
+    int debug;                  // EXPERIMENT ONLY: ablation bits
+    long long *trace;           // debug: per-role (tag, SM clock) records of block 0 (svr_debug_fq_trace), else null
 };
+
+// role 0: first gather warp, 1: MMA thread, 2: first epilogue warp, 3: weight loader
+__device__ __forceinline__ void fq_trace(const FqParams &p, int role, int &n, int tag) {
+    if (p.trace && blockIdx.x == 0 && n < 1024) {
+        p.trace[(role * 1024 + n) * 2] = tag;
+        p.trace[(role * 1024 + n) * 2 + 1] = clock64();
+        ++n;
+    }
+}
 
 constexpr int BRICK_X = 8, BRICK_Y = 4, BRICK_Z = 4;   // 128 lattice points per tile
 
@@ -102,6 +134,7 @@ struct FqSmem {
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *h_ready;
     uint32_t *tmem_ptr;
     uint32_t *utab;              // [FQ_UTAB] packed decode_unit results
+    WideGeo *wgeo;               // [SVR_MAX_LEVELS]
 };
 
 __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw) {
@@ -120,9 +153,68 @@ __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw) {
     s.h_ready = s.acc_full + 2;       // [1]
     s.tmem_ptr = (uint32_t *)(s.h_ready + 1);
     s.utab = (uint32_t *)((uint8_t *)bars + 512);
+    s.wgeo = (WideGeo *)((uint8_t *)s.utab + FQ_UTAB * 4);
     return s;
 }
 
+// ---- wide path ------------------------------------------------------------------------------------------------
+// Sample descriptor of one (row, stencil point) on a halo'd level: pointer to corner (z0, y0, x0) of channel 0 and the 8
+// trilinear weights.  Same index arithmetic and the same weights as gather_unit_fast; a corner outside the volume reads
+// a zero from the halo (fmaf(0, w, acc) == acc: the bits of the bounds-checked path), a sample whose cell lies entirely
+// outside (or a padding row) gets zero weights and a clamped in-range pointer.
+__device__ __forceinline__ void wide_desc(const WideGeo &G, int align, float dx, float dy, float dz, const float4 q,
+                                          const __nv_bfloat16 *&ptr, float (&w)[8]) {
+    const int scene = __float_as_int(q.w);
+    const float ix = unnorm(__fadd_rn(__fmul_rn(2.0f, q.z), dx), G.fw, align);
+    const float iy = unnorm(__fadd_rn(__fmul_rn(2.0f, q.y), dy), G.fh, align);
+    const float iz = unnorm(__fadd_rn(__fmul_rn(2.0f, q.x), dz), G.fd, align);
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const bool valid = scene >= 0 && fx >= -1.0f && fx <= G.fw - 1.0f && fy >= -1.0f && fy <= G.fh - 1.0f && fz >= -1.0f &&
+                       fz <= G.fd - 1.0f;                                        // NaN coordinates compare false
+    const int x0 = (int)fminf(fmaxf(fx, -1.0f), G.fw - 1.0f) + 1;               // halo coordinates; fmaxf(NaN, -1) = -1
+    const int y0 = (int)fminf(fmaxf(fy, -1.0f), G.fh - 1.0f) + 1;
+    const int z0 = (int)fminf(fmaxf(fz, -1.0f), G.fd - 1.0f) + 1;
+    const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+    const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+    const float wz1 = valid ? iz - fz : 0.f, wz0 = valid ? (fz + 1.0f) - iz : 0.f;
+    const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = wxy[k & 3] * ((k & 4) ? wz1 : wz0);
+    ptr = G.base + (long long)(scene < 0 ? 0 : scene) * G.scene + (z0 * G.sz + y0 * G.sy + x0 * G.C);
+}
+
+// 8 channels (one 16-byte unit) of one sample: 8 corner loads at compile-time (OC != 0) or run-time offsets, FFMA2 blend
+// in corner order from a zero accumulator (the arithmetic of gather_unit_fast), bf16 pack
+template <int OC, int OY, int OZ>
+__device__ __forceinline__ uint4 wide_blend(const __nv_bfloat16 *ptr, const float (&w)[8], int oc, int oy, int oz) {
+    const int ex = OC ? OC : oc, ey = OC ? OY : oy, ez = OC ? OZ : oz;
+    uint4 raw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        raw[k] = __ldg(reinterpret_cast<const uint4 *>(ptr + (((k & 1) ? ex : 0) + ((k & 2) ? ey : 0) + ((k & 4) ? ez : 0))));
+    unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        ffma2(acc[0], raw[k].x, w[k]);
+        ffma2(acc[1], raw[k].y, w[k]);
+        ffma2(acc[2], raw[k].z, w[k]);
+        ffma2(acc[3], raw[k].w, w[k]);
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        out[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// halo'd strides of the 128-net's wide levels on a 128^3 scene: 64 ch @ 32^3, 128 ch @ 16^3, 128 ch @ 8^3
+constexpr int WS1_C = 64, WS1_Y = 34 * 64, WS1_Z = 34 * 34 * 64;
+constexpr int WS2_C = 128, WS2_Y = 18 * 128, WS2_Z = 18 * 18 * 128;
+constexpr int WS3_C = 128, WS3_Y = 10 * 128, WS3_Z = 10 * 10 * 128;
 
 template <int FQ_GATHER_WARPS>
 __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_kernel(const FqParams p, int64_t n_tiles) {
@@ -148,6 +240,26 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
     }
     if (warp == 5) tmem_alloc(s.tmem_ptr, 512);
     for (int u = threadIdx.x; u < KC0 * 8; u += blockDim.x) s.utab[u] = pack_unit(p.P, u);
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + SVR_MAX_LEVELS) {
+        const int l = threadIdx.x - 32;
+        WideGeo g{};
+        if (l >= p.wide_level0 && l < p.P.n_levels) {
+            g.fw = (float)p.P.W[l];
+            g.fh = (float)p.P.H[l];
+            g.fd = (float)p.P.D[l];
+            g.C = p.P.C[l];
+            g.sy = (p.P.W[l] + 2) * g.C;
+            g.sz = (p.P.H[l] + 2) * g.sy;
+            g.cpd = g.C / 64;
+            g.chunk0 = p.P.ubase[l] / 8;
+            g.scene = (long long)(p.P.D[l] + 2) * g.sz;
+            g.base = p.halo.v[l];
+            if (g.C == WS1_C && g.sy == WS1_Y && g.sz == WS1_Z) g.spec = 1;
+            if (g.C == WS2_C && g.sy == WS2_Y && g.sz == WS2_Z) g.spec = 2;
+            if (g.C == WS3_C && g.sy == WS3_Y && g.sz == WS3_Z) g.spec = 3;
+        }
+        s.wgeo[l] = g;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,6 +275,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
         const int gt = threadIdx.x - 6 * 32;          // 0..255
         const int unit_in_chunk = gt & 7;
         uint32_t gc = 0;                              // global A-chunk counter
+        int tn = 0;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t tile = blockIdx.x + it * gridDim.x;
             float4 *pts_s = s.pts + (it & 1) * FQ_TILE;
@@ -174,7 +287,8 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 pts_s[gt] = make_float4(px, py, pz, __int_as_float(oi < 0 ? -1 : scene));
             }
             named_bar_sync(1, FQ_GATHER_THREADS);
-            for (int kc = 0; kc < KC0; ++kc, ++gc) {
+            // ---- generic chunks (levels without a halo'd copy, alignment padding, the tail) -----------------------
+            auto generic_chunk = [&](int kc) {
                 const int st = gc % FQ_NA;
                 const int u = kc * 8 + unit_in_chunk;
                 UnitCtx uc;
@@ -199,7 +313,9 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     }
                 };
                 mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
+                if (gt == 0) fq_trace(p, 0, tn, 100 + kc);
                 uint8_t *a_st = s.a + st * FQ_A_BYTES;
+                if (!(p.debug & 4))
 #pragma unroll 2
                 for (int r = gt >> 3; r < FQ_TILE; r += FQ_GATHER_THREADS / 8) {
                     const float4 q = pts_s[r];
@@ -233,7 +349,58 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s.a_full + st);
+                if (gt == 0) fq_trace(p, 0, tn, 200 + kc);
+                ++gc;
+            };
+            const int wide_c0 = p.wide_level0 < p.P.n_levels ? p.P.ubase[p.wide_level0] / 8 : KC0;
+            int kc = 0;
+            for (; kc < wide_c0; ++kc) generic_chunk(kc);
+            // ---- wide levels: descriptor per (row, stencil point), reused over the level's channel groups ----------
+            constexpr int ROWS = FQ_TILE / (FQ_GATHER_THREADS / 8);
+            for (int l = p.wide_level0; l < p.P.n_levels; ++l) {
+                const WideGeo G = s.wgeo[l];
+#pragma unroll 1
+                for (int d = 0; d < 7; ++d) {
+                    const float sgn = (d & 1) ? -p.P.delta : p.P.delta;
+                    const float dx = (d == 1 || d == 2) ? sgn : 0.f, dy = (d == 3 || d == 4) ? sgn : 0.f, dz = (d == 5 || d == 6) ? sgn : 0.f;
+                    const __nv_bfloat16 *ptr[ROWS];
+                    float w[ROWS][8];
+#pragma unroll
+                    for (int j = 0; j < ROWS; ++j)
+                        wide_desc(G, p.P.align, dx, dy, dz, pts_s[(gt >> 3) + j * (FQ_GATHER_THREADS / 8)], ptr[j], w[j]);
+#pragma unroll 1
+                    for (int h = 0; h < G.cpd; ++h, ++kc, ++gc) {
+                        const int st = gc % FQ_NA;
+                        const int goff = (h * 8 + unit_in_chunk) * 8;          // first channel of this thread's group
+                        mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
+                        if (gt == 0) fq_trace(p, 0, tn, 100 + kc);
+                        uint8_t *a_st = s.a + st * FQ_A_BYTES;
+                        if (!(p.debug & 8))
+#pragma unroll
+                        for (int j = 0; j < ROWS; ++j) {
+                            const int r = (gt >> 3) + j * (FQ_GATHER_THREADS / 8);
+                            uint4 val;
+                            switch (G.spec) {
+                                case 1: val = wide_blend<WS1_C, WS1_Y, WS1_Z>(ptr[j] + goff, w[j], 0, 0, 0); break;
+                                case 2: val = wide_blend<WS2_C, WS2_Y, WS2_Z>(ptr[j] + goff, w[j], 0, 0, 0); break;
+                                case 3: val = wide_blend<WS3_C, WS3_Y, WS3_Z>(ptr[j] + goff, w[j], 0, 0, 0); break;
+                                default: val = wide_blend<0, 0, 0>(ptr[j] + goff, w[j], G.C, G.sy, G.sz); break;
+                            }
+                            *reinterpret_cast<uint4 *>(a_st + swz128(r, unit_in_chunk)) = val;
+                            if (p.save_feat) {
+                                const int64_t row = tile * FQ_TILE + r;
+                                if (row < p.total)
+                                    *reinterpret_cast<uint4 *>(p.save_feat + row * p.P.kp + (int64_t)(kc * 8 + unit_in_chunk) * 8) = val;
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s.a_full + st);
+                        if (gt == 0) fq_trace(p, 0, tn, 200 + kc);
+                    }
+                }
             }
+            for (; kc < KC0; ++kc) generic_chunk(kc);      // zero padding up to KP
         }
     } else if (warp == 4) {
         // ======================= weight loader =======================
@@ -247,6 +414,10 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     const uint8_t *src = c < KC0 ? p.w0_img + (size_t)c * FQ_B_BYTES
                                                  : (c < KC0 + 4 ? p.w1_img + (size_t)(c - KC0) * FQ_B_BYTES
                                                                 : p.w2_img + (size_t)(c - KC0 - 4) * FQ_B_BYTES);
+                    if (p.debug & 2) {
+                        mbar_arrive(s.b_full + st);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(s.b_full + st, FQ_B_BYTES);
                     bulk_g2s(smem_u32(s.b + st * FQ_B_BYTES), src, FQ_B_BYTES, s.b_full + st);
                 }
@@ -257,6 +428,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
         if (lane == 0 && my_tiles > 0) {
             const uint32_t idesc = make_idesc_bf16(FQ_TILE, FQ_HID, 0, 0);
             uint32_t gc = 0, wc = 0, hr = 0;
+            int tn = 0;
             auto wait_b = [&]() {
                 const int st = wc % FQ_NB;
                 mbar_wait(s.b_full + st, (wc / FQ_NB) & 1);
@@ -266,7 +438,9 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 for (int kc = 0; kc < KC0; ++kc, ++gc) {
                     const int sa = gc % FQ_NA;
                     mbar_wait(s.a_full + sa, (gc / FQ_NA) & 1);
+                    fq_trace(p, 1, tn, 300 + kc);
                     const int sb = wait_b();
+                    fq_trace(p, 1, tn, 400 + kc);
                     tc_fence_after();
                     const uint32_t a_s = smem_u32(s.a + sa * FQ_A_BYTES), b_s = smem_u32(s.b + sb * FQ_B_BYTES);
 #pragma unroll
@@ -281,6 +455,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
             };
             auto issue_hidden = [&]() {   // A = H tile (4 K-chunks), B = next 4 weight chunks, D = acc1
                 mbar_wait(s.h_ready, hr & 1);
+                fq_trace(p, 1, tn, 500 + (int)(hr & 1));
                 ++hr;
                 tc_fence_after();
                 for (int kc = 0; kc < 4; ++kc) {
@@ -311,6 +486,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
         const int r = warp * 32 + lane;            // row in tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         uint32_t n0 = 0, n1 = 0;                   // completions consumed of acc_full[0], acc_full[1]
+        int tn = 0;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t tile = blockIdx.x + it * gridDim.x;
             float px, py, pz;
@@ -331,6 +507,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     ++n1;
                 }
                 tc_fence_after();
+                if (threadIdx.x == 0) fq_trace(p, 2, tn, 600 + layer);
                 const uint32_t acc = (layer == 0 ? acc0 : acc1) + lane_off;
 #pragma unroll 1
                 for (int c0 = 0; c0 < FQ_HID; c0 += 32) {
@@ -370,6 +547,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s.h_ready);
                 }
+                if (threadIdx.x == 0) fq_trace(p, 2, tn, 610 + layer);
             }
             if (row_ok) {
                 float logit = dot + __ldg(p.bout);
@@ -397,8 +575,8 @@ __global__ void swizzle_image_kernel(const __nv_bfloat16 *__restrict__ src, int 
     *reinterpret_cast<uint4 *>(dst + (size_t)chunk * R * 128 + tc::swz128(row, uc)) = v;
 }
 
-static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_host, const svr_pyramid *pyr_host,
-                   const svr_decoder_weights *w) {
+static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_host, const uint16_t *const *halo_host,
+                   const svr_pyramid *pyr_host, const svr_decoder_weights *w) {
     if (int rc = make_pyr(p.P, pyr_host)) return rc;
     SVR_REQUIRE(w && x0 && vols_host, "fused query: null pointer");
     SVR_REQUIRE(w->h0 == FQ_HID && w->h1 == FQ_HID && w->h2 == FQ_HID, "fused query supports hidden size 256 only (got %d/%d/%d)",
@@ -408,6 +586,19 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
     for (int l = 0; l < SVR_MAX_LEVELS; ++l) {
         p.vols.v[l] = (l >= 1 && l < p.P.n_levels) ? (const __nv_bfloat16 *)vols_host[l] : nullptr;
         SVR_REQUIRE(!(l >= 1 && l < p.P.n_levels) || p.vols.v[l], "fused query: volume of level %d is null", l);
+    }
+    // wide path: the trailing run of levels with C % 64 == 0 (chunk-aligned by make_pyr) that come with a halo'd copy
+    p.wide_level0 = p.P.n_levels;
+    for (int l = 0; l < SVR_MAX_LEVELS; ++l) p.halo.v[l] = nullptr;
+    if (halo_host) {
+        for (int l = p.P.n_levels - 1; l >= 1; --l) {
+            if (p.P.C[l] % 64 != 0 || !halo_host[l]) break;
+            SVR_REQUIRE(((uintptr_t)halo_host[l] & 15) == 0, "fused query: halo volume of level %d is not 16-byte aligned", l);
+            SVR_REQUIRE((int64_t)(p.P.D[l] + 2) * (p.P.H[l] + 2) * (p.P.W[l] + 2) * p.P.C[l] < ((int64_t)1 << 31),
+                        "fused query: halo volume of level %d exceeds 2^31 elements per scene", l);
+            p.halo.v[l] = (const __nv_bfloat16 *)halo_host[l];
+            p.wide_level0 = l;
+        }
     }
     p.x0 = x0;
     p.w0_img = (const uint8_t *)w->w0p;
@@ -421,16 +612,25 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
     return 0;
 }
 
+static long long *g_fq_trace = nullptr;
+
 static int fq_launch(const FqParams &p, int64_t n_tiles, cudaStream_t st) {
     static DeviceOnce once;
     int dev;
     if (once.needed(dev)) {
         SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
+        SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
         once.done(dev);
     }
     if (n_tiles <= 0) return 0;
     int grid = sm_count();
     if (n_tiles < grid) grid = (int)n_tiles;
+    static const int gw = getenv("SVR_FQ_GW") ? atoi(getenv("SVR_FQ_GW")) : 16;     // EXPERIMENT ONLY
+    const_cast<FqParams &>(p).debug = getenv("SVR_FQ_DEBUG") ? atoi(getenv("SVR_FQ_DEBUG")) : 0;
+    const_cast<FqParams &>(p).trace = g_fq_trace;
+    if (gw == 8)
+        fused_query_kernel<8><<<grid, fq_threads(8), FQ_SMEM, st>>>(p, n_tiles);
+    else
     fused_query_kernel<16><<<grid, fq_threads(16), FQ_SMEM, st>>>(p, n_tiles);
     SVR_LAUNCH_CHECK();
     return 0;
@@ -442,6 +642,12 @@ using namespace svr;
 
 extern "C" {
 
+/* debug: per-role (tag, SM clock) records of block 0 of the next fused query launches; buf = 4 x 1024 x 2 int64 (device), null = off */
+int svr_debug_fq_trace(void *buf) {
+    g_fq_trace = (long long *)buf;
+    return 0;
+}
+
 int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *image, void *stream) {
     SVR_REQUIRE(w_rowmajor && image && R > 0 && K > 0 && K % 64 == 0 && R % 8 == 0, "pack_decoder_image: R %% 8 == 0 and K %% 64 == 0 required");
     int64_t units = (int64_t)R * (K / 8);
@@ -452,10 +658,10 @@ int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *im
 }
 
 int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, const float *x0, const uint16_t *const *vols_host,
-                        const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, float *logits, uint16_t *save_h,
-                        uint16_t *save_feat, int apply_sigmoid, void *stream) {
+                        const uint16_t *const *halo_vols_host, const svr_pyramid *pyr_host, const svr_decoder_weights *w_host,
+                        float *logits, uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream) {
     FqParams p{};
-    if (int rc = fq_fill(p, x0, vols_host, pyr_host, w_host)) return rc;
+    if (int rc = fq_fill(p, x0, vols_host, halo_vols_host, pyr_host, w_host)) return rc;
     SVR_REQUIRE(points && logits, "query_fwd_fused: null pointer");
     p.points = points;
     p.perm = perm;
@@ -468,10 +674,11 @@ int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, cons
     return fq_launch(p, ceil_div<int64_t>(p.total, FQ_TILE), as_stream(stream));
 }
 
-int svr_dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host, const svr_pyramid *pyr_host,
-                   const svr_decoder_weights *w_host, int sx, int sy, int sz, int x_begin, int x_end, float *out, void *stream) {
+int svr_dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host,
+                   const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, int sx, int sy, int sz, int x_begin, int x_end,
+                   float *out, void *stream) {
     FqParams p{};
-    if (int rc = fq_fill(p, x0, vols_host, pyr_host, w_host)) return rc;
+    if (int rc = fq_fill(p, x0, vols_host, halo_vols_host, pyr_host, w_host)) return rc;
     SVR_REQUIRE(out && scene >= 0 && scene < B, "dense_eval: bad scene index");
     SVR_REQUIRE(sx > 0 && sy > 0 && sz > 0 && x_begin >= 0 && x_end <= sx && x_begin <= x_end, "dense_eval: bad lattice range");
     p.points = nullptr;

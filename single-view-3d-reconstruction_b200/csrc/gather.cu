@@ -206,6 +206,37 @@ __global__ void __launch_bounds__(256) convert_bf16_kernel(const float *__restri
     }
 }
 
+// fp32 (B,C,D,H,W) with arbitrary strides -> bf16 (B, D+2, H+2, W+2, C) with a one-voxel ZERO halo: the wide path of the
+// fused query kernel reads the zeros of grid_sample's zero padding from the halo instead of testing every corner.
+// thread = (halo'd voxel, 8-channel group); only used for the coarse levels (a few MB per scene)
+__global__ void __launch_bounds__(256) pack_volume_halo_kernel(const float *__restrict__ src, int C, int D, int H, int W, int64_t total,
+                                                               int64_t sB, int64_t sC, int64_t sD, int64_t sH, int64_t sW,
+                                                               __nv_bfloat16 *__restrict__ dst) {
+    const int cg = C / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        int64_t v = i / cg;
+        const int x = (int)(v % (W + 2)) - 1;
+        v /= (W + 2);
+        const int y = (int)(v % (H + 2)) - 1;
+        v /= (H + 2);
+        const int z = (int)(v % (D + 2)) - 1;
+        const int64_t b = v / (D + 2);
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (x >= 0 && y >= 0 && z >= 0 && x < W && y < H && z < D) {
+            const float *sp = src + b * sB + z * sD + y * sH + x * sW + (int64_t)g * 8 * sC;
+            if (sC == 1 && (((uintptr_t)sp) & 15) == 0) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(sp)), c = __ldg(reinterpret_cast<const float4 *>(sp) + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c.x; f[5] = c.y; f[6] = c.z; f[7] = c.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __ldg(sp + j * sC);
+            }
+        }
+        reinterpret_cast<uint4 *>(dst)[i] = float8_to_bf16(f);
+    }
+}
+
 // fp32 NDHWC -> (+)= strided fp32 (B,C,D,H,W)
 __global__ void __launch_bounds__(256) unpack_volume_grad_kernel(const float *__restrict__ src, int C, int D, int H, int W,
                                                                  int64_t spatial_total, int64_t sB, int64_t sC, int64_t sD,
@@ -302,6 +333,20 @@ int svr_pack_volume(const float *src, int B, int C, int D, int H, int W, int64_t
     size_t smem = (size_t)C * 33 * sizeof(float);
     pack_volume_kernel<<<(unsigned)ceil_div<int64_t>(spatial, 32), 256, smem, as_stream(stream)>>>(
         src, C, D, H, W, spatial, sB, sC, sD, sH, sW, (__nv_bfloat16 *)dst);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
+int svr_pack_volume_halo(const float *src, int B, int C, int D, int H, int W, int64_t sB, int64_t sC, int64_t sD, int64_t sH,
+                         int64_t sW, uint16_t *dst, void *stream) {
+    SVR_REQUIRE(src && dst, "pack_volume_halo: null pointer");
+    SVR_REQUIRE(C > 0 && C % 8 == 0, "pack_volume_halo: C must be a positive multiple of 8");
+    SVR_REQUIRE(((uintptr_t)dst & 15) == 0, "pack_volume_halo: dst must be 16-byte aligned");
+    const int64_t total = (int64_t)B * (D + 2) * (H + 2) * (W + 2) * (C / 8);
+    if (total == 0) return 0;
+    int64_t blocks = ceil_div<int64_t>(total, 256), cap = (int64_t)sm_count() * 16;
+    pack_volume_halo_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(src, C, D, H, W, total, sB, sC, sD, sH, sW,
+                                                                                                 (__nv_bfloat16 *)dst);
     SVR_LAUNCH_CHECK();
     return 0;
 }

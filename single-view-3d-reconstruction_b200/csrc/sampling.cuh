@@ -147,17 +147,23 @@ __device__ __forceinline__ uint4 float8_to_bf16(const float (&f)[8]) {
 __device__ __forceinline__ float level0_sample(const Pyr &P, int dd, float px, float py, float pz, const float *__restrict__ x0_b) {
     Corners c;
     stencil_corners(P, 0, dd, px, py, pz, c);
+    // branch-free: all 8 (clamped, always valid) loads are issued back to back -- with a branch per corner the
+    // loads of this 33 MB/scene fp32 grid were serialised into 8 dependent DRAM round trips per sample
+    float v[8];
+    bool in[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int x = c.x0 + (k & 1), y = c.y0 + ((k >> 1) & 1), z = c.z0 + (k >> 2);
+        in[k] = corner_in(P, 0, x, y, z);
+        const int xc = min(max(x, 0), P.W[0] - 1), yc = min(max(y, 0), P.H[0] - 1), zc = min(max(z, 0), P.D[0] - 1);
+        v[k] = __ldg(x0_b + ((int64_t)zc * P.H[0] + yc) * P.W[0] + xc);
+    }
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < 2; ++e)
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int aa = 0; aa < 2; ++aa) {
-                int x = c.x0 + aa, y = c.y0 + b, z = c.z0 + e;
-                if (corner_in(P, 0, x, y, z))
-                    a += __ldg(x0_b + ((int64_t)z * P.H[0] + y) * P.W[0] + x) * (c.wx[aa] * c.wy[b] * c.wz[e]);
-            }
+    for (int k = 0; k < 8; ++k) {     // same order and the same fused multiply-adds as the per-corner form
+        const float w = c.wx[k & 1] * c.wy[(k >> 1) & 1] * c.wz[k >> 2];
+        a = in[k] ? fmaf(v[k], w, a) : a;
+    }
     return a;
 }
 

@@ -518,6 +518,35 @@ def pack_volume(v: torch.Tensor) -> torch.Tensor:
     return out
 
 
+USE_HALO = True      # halo'd copies of the wide levels for the fused kernel's bounds-check-free path
+
+
+@_entry
+def pack_volume_halo(v: torch.Tensor) -> torch.Tensor:
+    """fp32 (B,C,D,H,W), any strides -> bf16 (B, D+2, H+2, W+2, C) with a one-voxel zero halo."""
+    if not v.is_cuda:
+        raise RuntimeError("svr_b200: feature volumes must be CUDA tensors; there is no CPU path")
+    if v.dtype != torch.float32:
+        v = v.float()
+    B, Cc, D, H, W = v.shape
+    out = torch.empty((B, D + 2, H + 2, W + 2, Cc), device=v.device, dtype=_BF16)
+    s = v.stride()
+    _abi.check(_lib().svr_pack_volume_halo(v.data_ptr(), B, Cc, D, H, W, s[0], s[1], s[2], s[3], s[4], out.data_ptr(), _stream()),
+               "pack_volume_halo")
+    return out
+
+
+def halo_volumes(vols):
+    """Halo'd copies of the trailing run of levels with C % 64 == 0 (None for the others)."""
+    out = [None] * len(vols)
+    if USE_HALO:
+        for i in range(len(vols) - 1, -1, -1):
+            if vols[i].shape[1] % 64 != 0:
+                break
+            out[i] = pack_volume_halo(vols[i])
+    return out
+
+
 class PackedDecoder:
     """bf16 copies of the decoder weights in kernel layout.  Re-packed on EVERY call (three tiny
     kernels, ~10 us) unless ``frozen`` is set: fused optimisers update parameters without bumping
@@ -599,7 +628,7 @@ def sort_points(pts: torch.Tensor) -> torch.Tensor:
     return perm
 
 
-def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, sigmoid: bool = False, perm=None):
+def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, sigmoid: bool = False, perm=None, halo=None):
     """One launch: gather -> tcgen05 decoder.  Returns (logits (M,), h (3,M,256) or None, feat (M,KP) or None)."""
     B, N, _ = pts.shape
     M = B * N
@@ -613,7 +642,8 @@ def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, 
     h = torch.empty((3, M, 256), device=dev, dtype=_BF16) if save else None
     feat = torch.empty((M, pyr.kp), device=dev, dtype=_BF16) if save else None
     tbl = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
-    _abi.check(_lib().svr_query_fwd_fused(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), tbl, C.byref(pyr.c), C.byref(dw),
+    htbl = _abi.ptr_table([None] + [_ptr(v) for v in (halo or [])])
+    _abi.check(_lib().svr_query_fwd_fused(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), tbl, htbl, C.byref(pyr.c), C.byref(dw),
                                           logits.data_ptr(), _ptr(h), _ptr(feat), int(sigmoid), _stream()), "query_fwd_fused")
     return logits, h, feat
 
@@ -655,10 +685,12 @@ def dense_eval(pyr, cache, x, vols, w0, b0, w1, b1, w2, b2, wo, bo, lattice, sce
     wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
     dw = _decoder_struct(W, b0f, b1f, b2f, wof, bof)
     tbl = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
+    halo = halo_volumes(vols)
+    htbl = _abi.ptr_table([None] + [_ptr(v) for v in halo])
     xb, xe = (0, sx) if x_range is None else x_range
     out = torch.zeros((len(scenes), sx, sy, sz), device=x0.device, dtype=torch.float32)
     for i, sc in enumerate(scenes):
-        _abi.check(_lib().svr_dense_eval(int(sc), x0.shape[0], x0.data_ptr(), tbl, C.byref(pyr.c), C.byref(dw), sx, sy, sz, int(xb), int(xe),
+        _abi.check(_lib().svr_dense_eval(int(sc), x0.shape[0], x0.data_ptr(), tbl, htbl, C.byref(pyr.c), C.byref(dw), sx, sy, sz, int(xb), int(xe),
                                          out[i].data_ptr(), _stream()), "dense_eval")
     return out
 
@@ -671,7 +703,7 @@ class _Query(torch.autograd.Function):
 
     @staticmethod
     @_entry
-    def forward(ctx, pyr: PyramidSpec, cache: PackedDecoder, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
+    def forward(ctx, pyr: PyramidSpec, cache: PackedDecoder, grad_mode: bool, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
         pts = _dev_f32(points, "points")
         x0 = _dev_f32(x, "x")
         B, N, _ = pts.shape
@@ -682,12 +714,15 @@ class _Query(torch.autograd.Function):
         h0n, h1n, h2n = w0.shape[0], w1.shape[0], w2.shape[0]
         b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
         wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
-        needs_bwd = any(ctx.needs_input_grad)
+        # needs_input_grad is set for parameters even under torch.no_grad(); nothing is saved (and the kernels skip the
+        # 1.3 GB of feature / activation stores per 200k points) unless a graph is being recorded
+        needs_bwd = bool(grad_mode) and any(ctx.needs_input_grad)
         perm = None
         if USE_FUSED and "w0p_img" in W:
             if N >= SORT_MIN_POINTS:
                 perm = sort_points(pts)
-            logits, hs, feat = fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save=needs_bwd, perm=perm)
+            logits, hs, feat = fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save=needs_bwd, perm=perm,
+                                             halo=halo_volumes(vols))
             if not needs_bwd:
                 return logits.view(B, N)
             h0, h1, h2 = hs[0], hs[1], hs[2]
@@ -701,8 +736,8 @@ class _Query(torch.autograd.Function):
             _gemm_nt(h0, W["w1"], b1f, M, h1n, h0n, RELU | ST_BF16, c_bf16=h1, ldc=h1n)
             _gemm_nt(h1, W["w2"], b2f, M, h2n, h1n, RELU | ST_BF16 | DOT, c_bf16=h2, ldc=h2n, dot_w=wof, dot_b=bof, out_dot=logits)
         ctx.pyr, ctx.cache_t = pyr, W
-        ctx.vol_meta = [(v.shape, v.stride(), ctx.needs_input_grad[12 + i]) for i, v in enumerate(vols)]
-        ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[3], ctx.needs_input_grad[2]
+        ctx.vol_meta = [(v.shape, v.stride(), ctx.needs_input_grad[13 + i]) for i, v in enumerate(vols)]
+        ctx.x_needs, ctx.p_needs = ctx.needs_input_grad[4], ctx.needs_input_grad[3]
         ctx.shapes = (B, N, w0.shape, w1.shape, w2.shape, wo.shape)
         ctx.has_perm = perm is not None
         ctx.save_for_backward(pts, x0, feat, h0, h1, h2, wof, perm if perm is not None else pts.new_empty(0), *packed)
@@ -936,7 +971,7 @@ def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols, precision
         return points.new_zeros((points.shape[0], points.shape[1]), dtype=torch.float32)
     if int(precision) == 32:
         return _Query32.apply(pyr, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
-    return _Query.apply(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
+    return _Query.apply(pyr, cache, torch.is_grad_enabled(), points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
 
 
 class _Gather(torch.autograd.Function):
