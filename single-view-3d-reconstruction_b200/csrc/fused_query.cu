@@ -16,8 +16,10 @@
 //               descriptor (corner base pointer + 8 trilinear weights, no bounds logic: the halo supplies the
 //               zeros of grid_sample's zero padding) is computed once per (row, stencil point) and reused for all
 //               the level's channel groups of the thread (C/64 consecutive K chunks).
-// TMEM: acc0 = columns [0,256) (fc_0), acc1 = [256,512) (fc_1 and fc_2).  Issue order per tile i:
-//   F1(i) | F0(i+1) | F2(i)   so that the long fc_0 of the next tile overlaps this tile's epilogues.
+// TMEM (512 columns): [0,256) the fp32 accumulator of whichever layer is running, [256,384) H0 = relu(fc_0) and
+// [384,512) H1 = relu(fc_1) as packed bf16 pairs: the hidden activations never touch shared memory -- the epilogue writes
+// them with tcgen05.st and fc_1 / fc_2 read them as the TMEM A operand of tcgen05.mma (the 64 KB H tile of round 1 is
+// gone: shared memory 221 -> 157 KB, which the hardware hands to the L1 data cache the gather loads go through).
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tc05.cuh"
@@ -28,15 +30,20 @@ using namespace tc;
 
 constexpr int FQ_TILE = 128;
 constexpr int FQ_HID = 256;
-constexpr int FQ_NA = 3, FQ_NB = 3;
+constexpr int FQ_NA = 3, FQ_NB = 2, FQ_NB_MAX = 4;      // FQ_NB: default weight-ring depth (p.nb at run time; 2: 1.03 ms, 3: 1.04, 4: 1.10 -- L1 capacity)
 constexpr int FQ_A_BYTES = FQ_TILE * 128;        // 16 KB: 128 rows x 64 bf16
 constexpr int FQ_B_BYTES = FQ_HID * 128;         // 32 KB: 256 rows x 64 bf16
-constexpr int FQ_H_BYTES = FQ_TILE * FQ_HID * 2; // 64 KB: 4 K-chunks of 16 KB
+constexpr int FQ_BIAS_BYTES = 4 * FQ_HID * 4;    // b0, b1, b2, wout as fp32 in shared memory (epilogue operands)
 constexpr int FQ_EPI_WARPS = 4;
 constexpr int fq_threads(int gather_warps) { return (FQ_EPI_WARPS + 2 + gather_warps) * 32; }   // 448 for 8 gather warps
 constexpr int FQ_UTAB = 512;                     // unit table entries (KP <= 4096)
 constexpr int FQ_WGEO_BYTES = 512;               // per-level geometry of the wide path
-constexpr int FQ_SMEM = 1024 + FQ_NA * FQ_A_BYTES + FQ_NB * FQ_B_BYTES + FQ_H_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4 + FQ_WGEO_BYTES;
+// Shared memory is kept SMALL on purpose: what a CTA does not request stays L1 data cache (228 KB - shared memory per SM),
+// and the gather lives on L1 hits -- neighbouring (spatially sorted) rows and the 7 stencil points of a row read the same
+// voxels.  Staging the corner loads through shared memory (cp.async, one 128-byte slot per thread: latency fully hidden, no
+// registers in flight) was measured SLOWER (1.39 vs 1.02 ms at config 2) because its 64 KB shrink L1 to a few KB.
+constexpr int fq_smem(int nb) { return 1024 + FQ_NA * FQ_A_BYTES + nb * FQ_B_BYTES + FQ_BIAS_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4 + FQ_WGEO_BYTES; }
+constexpr int FQ_SMEM = fq_smem(FQ_NB_MAX);
 
 // geometry of one WIDE level (C % 64 == 0) sampled from its halo'd copy (B, D+2, H+2, W+2, C), see the header comment
 struct WideGeo {
@@ -74,6 +81,7 @@ struct FqParams {
     __nv_bfloat16 *save_feat;   // optional (total, KP)
     int apply_sigmoid;
     int debug;                  // EXPERIMENT ONLY: ablation bits
+    int nb;                     // weight-ring depth (2..FQ_NB_MAX)
     long long *trace;           // debug: per-role (tag, SM clock) records of block 0 (svr_debug_fq_trace), else null
 };
 
@@ -129,29 +137,31 @@ __device__ __forceinline__ void row_point(const FqParams &p, int64_t tile, int r
 }
 
 struct FqSmem {
-    uint8_t *a, *b, *h;
+    uint8_t *a, *b;
+    float *bias;                 // [4][256]: b0, b1, b2, wout
     float4 *pts;                 // [2][128] : (px,py,pz, scene as int bits)
-    uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *h_ready;
+    uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *h_ready, *acc_free;
     uint32_t *tmem_ptr;
     uint32_t *utab;              // [FQ_UTAB] packed decode_unit results
     WideGeo *wgeo;               // [SVR_MAX_LEVELS]
 };
 
-__device__ __forceinline__ FqSmem fq_carve(uint8_t *raw) {
+__device__ __forceinline__ FqSmem fq_carve(uint8_t *raw, int nb) {
     FqSmem s;
     uint8_t *base = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     s.a = base;
     s.b = s.a + FQ_NA * FQ_A_BYTES;
-    s.h = s.b + FQ_NB * FQ_B_BYTES;
-    s.pts = (float4 *)(s.h + FQ_H_BYTES);
+    s.bias = (float *)(s.b + nb * FQ_B_BYTES);
+    s.pts = (float4 *)((uint8_t *)s.bias + FQ_BIAS_BYTES);
     uint64_t *bars = (uint64_t *)(s.pts + 2 * FQ_TILE);
     s.a_full = bars;
     s.a_empty = s.a_full + FQ_NA;
     s.b_full = s.a_empty + FQ_NA;
-    s.b_empty = s.b_full + FQ_NB;
-    s.acc_full = s.b_empty + FQ_NB;   // [2]
-    s.h_ready = s.acc_full + 2;       // [1]
-    s.tmem_ptr = (uint32_t *)(s.h_ready + 1);
+    s.b_empty = s.b_full + FQ_NB_MAX;
+    s.acc_full = s.b_empty + FQ_NB_MAX;   // [1] accumulator complete (every layer)
+    s.h_ready = s.acc_full + 2;       // [1] hidden activations written to TMEM
+    s.acc_free = s.h_ready + 1;       // [1] accumulator drained by the last epilogue of a tile
+    s.tmem_ptr = (uint32_t *)(s.acc_free + 1);
     s.utab = (uint32_t *)((uint8_t *)bars + 512);
     s.wgeo = (WideGeo *)((uint8_t *)s.utab + FQ_UTAB * 4);
     return s;
@@ -220,7 +230,8 @@ template <int FQ_GATHER_WARPS>
 __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_kernel(const FqParams p, int64_t n_tiles) {
     constexpr int FQ_GATHER_THREADS = FQ_GATHER_WARPS * 32;
     extern __shared__ uint8_t smem_raw[];
-    const FqSmem s = fq_carve(smem_raw);
+    const FqSmem s = fq_carve(smem_raw, p.nb);
+    const int NB = p.nb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KC0 = p.P.kp / 64;
 
@@ -229,17 +240,22 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
             mbar_init(s.a_full + i, FQ_GATHER_WARPS);
             mbar_init(s.a_empty + i, 1);
         }
-        for (int i = 0; i < FQ_NB; ++i) {
+        for (int i = 0; i < FQ_NB_MAX; ++i) {
             mbar_init(s.b_full + i, 1);
             mbar_init(s.b_empty + i, 1);
         }
         mbar_init(s.acc_full + 0, 1);
         mbar_init(s.acc_full + 1, 1);
         mbar_init(s.h_ready, FQ_EPI_WARPS);
+        mbar_init(s.acc_free, FQ_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc(s.tmem_ptr, 512);
     for (int u = threadIdx.x; u < KC0 * 8; u += blockDim.x) s.utab[u] = pack_unit(p.P, u);
+    for (int i = threadIdx.x; i < 4 * FQ_HID; i += blockDim.x) {
+        const float *src = i < FQ_HID ? p.b0 : (i < 2 * FQ_HID ? p.b1 : (i < 3 * FQ_HID ? p.b2 : p.wout));
+        s.bias[i] = src[i & (FQ_HID - 1)];
+    }
     if (threadIdx.x >= 32 && threadIdx.x < 32 + SVR_MAX_LEVELS) {
         const int l = threadIdx.x - 32;
         WideGeo g{};
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s.tmem_ptr;
-    const uint32_t acc0 = tmem, acc1 = tmem + 256;
+    const uint32_t acc0 = tmem, tm_h0 = tmem + 256, tm_h1 = tmem + 384;
 
     // number of tiles of this CTA
     int64_t my_tiles = 0;
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
 
     if (warp >= 6) {
         // ======================= gather producers =======================
-        const int gt = threadIdx.x - 6 * 32;          // 0..255
+        const int gt = threadIdx.x - 6 * 32;          // 0..511
         const int unit_in_chunk = gt & 7;
         uint32_t gc = 0;                              // global A-chunk counter
         int tn = 0;
@@ -409,8 +425,8 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
             for (int64_t it = 0; it < my_tiles; ++it) {
                 const int n_chunks = KC0 + 4 + 4;
                 for (int c = 0; c < n_chunks; ++c, ++wc) {
-                    const int st = wc % FQ_NB;
-                    mbar_wait(s.b_empty + st, ((wc / FQ_NB) & 1) ^ 1);
+                    const int st = wc % NB;
+                    mbar_wait(s.b_empty + st, ((wc / NB) & 1) ^ 1);
                     const uint8_t *src = c < KC0 ? p.w0_img + (size_t)c * FQ_B_BYTES
                                                  : (c < KC0 + 4 ? p.w1_img + (size_t)(c - KC0) * FQ_B_BYTES
                                                                 : p.w2_img + (size_t)(c - KC0 - 4) * FQ_B_BYTES);
@@ -430,17 +446,18 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
             uint32_t gc = 0, wc = 0, hr = 0;
             int tn = 0;
             auto wait_b = [&]() {
-                const int st = wc % FQ_NB;
-                mbar_wait(s.b_full + st, (wc / FQ_NB) & 1);
+                const int st = wc % NB;
+                mbar_wait(s.b_full + st, (wc / NB) & 1);
                 return st;
             };
-            auto issue_f0 = [&]() {
+            auto issue_f0 = [&](int64_t it) {
                 for (int kc = 0; kc < KC0; ++kc, ++gc) {
                     const int sa = gc % FQ_NA;
                     mbar_wait(s.a_full + sa, (gc / FQ_NA) & 1);
                     fq_trace(p, 1, tn, 300 + kc);
                     const int sb = wait_b();
                     fq_trace(p, 1, tn, 400 + kc);
+                    if (kc == 0 && it > 0) mbar_wait(s.acc_free, (uint32_t)(it - 1) & 1);   // previous tile's logits epilogue drained the accumulator
                     tc_fence_after();
                     const uint32_t a_s = smem_u32(s.a + sa * FQ_A_BYTES), b_s = smem_u32(s.b + sb * FQ_B_BYTES);
 #pragma unroll
@@ -451,33 +468,32 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     umma_commit(s.b_empty + sb);
                     ++wc;
                 }
-                umma_commit(s.acc_full + 0);
+                umma_commit(s.acc_full);
             };
-            auto issue_hidden = [&]() {   // A = H tile (4 K-chunks), B = next 4 weight chunks, D = acc1
-                mbar_wait(s.h_ready, hr & 1);
+            auto issue_hidden = [&](uint32_t tm_a) {   // A = hidden activations in TMEM (K = 256: 128 columns), B = next 4 weight chunks
+                mbar_wait(s.h_ready, hr & 1);          // the epilogue has also finished READING the accumulator these MMAs overwrite
                 fq_trace(p, 1, tn, 500 + (int)(hr & 1));
                 ++hr;
                 tc_fence_after();
                 for (int kc = 0; kc < 4; ++kc) {
                     const int sb = wait_b();
                     tc_fence_after();
-                    const uint32_t a_s = smem_u32(s.h + kc * FQ_A_BYTES), b_s = smem_u32(s.b + sb * FQ_B_BYTES);
+                    const uint32_t b_s = smem_u32(s.b + sb * FQ_B_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(acc1, make_smem_desc(a_s + k * 32, 16, 1024, kSwizzle128B),
-                                  make_smem_desc(b_s + k * 32, 16, 1024, kSwizzle128B), idesc, (kc | k) != 0);
+                        umma_bf16_ts(acc0, tm_a + (uint32_t)(kc * 4 + k) * 8, make_smem_desc(b_s + k * 32, 16, 1024, kSwizzle128B), idesc,
+                                     (kc | k) != 0);
                     umma_commit(s.b_empty + sb);
                     ++wc;
                 }
-                umma_commit(s.acc_full + 1);
+                umma_commit(s.acc_full);
             };
-            // The weight loader streams W0(i), W1(i), W2(i) per tile in that order, so the issue order
-            // must consume them in the same order: F0(i), F1(i), F2(i).  (Overlapping F0(i+1) with the
-            // epilogues of tile i needs a second weight ring; kept simple here.)
+            // The weight loader streams W0(i), W1(i), W2(i) per tile in that order; the issue order consumes them in the
+            // same order: F0(i), F1(i), F2(i).
             for (int64_t it = 0; it < my_tiles; ++it) {
-                issue_f0();
-                issue_hidden();
-                issue_hidden();
+                issue_f0(it);
+                issue_hidden(tm_h0);
+                issue_hidden(tm_h1);
             }
         }
         __syncwarp();
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
         // ======================= epilogue =======================
         const int r = warp * 32 + lane;            // row in tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-        uint32_t n0 = 0, n1 = 0;                   // completions consumed of acc_full[0], acc_full[1]
+        uint32_t n_acc = 0;                        // completions consumed of acc_full
         int tn = 0;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t tile = blockIdx.x + it * gridDim.x;
@@ -498,17 +514,14 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
             float dot = 0.f;
 #pragma unroll 1
             for (int layer = 0; layer < 3; ++layer) {
-                const float *bias = layer == 0 ? p.b0 : (layer == 1 ? p.b1 : p.b2);
-                if (layer == 0) {
-                    mbar_wait(s.acc_full + 0, n0 & 1);
-                    ++n0;
-                } else {
-                    mbar_wait(s.acc_full + 1, n1 & 1);
-                    ++n1;
-                }
+                const float4 *bias4 = reinterpret_cast<const float4 *>(s.bias + layer * FQ_HID);
+                const float4 *wout4 = reinterpret_cast<const float4 *>(s.bias + 3 * FQ_HID);
+                mbar_wait(s.acc_full, n_acc & 1);
+                ++n_acc;
                 tc_fence_after();
                 if (threadIdx.x == 0) fq_trace(p, 2, tn, 600 + layer);
-                const uint32_t acc = (layer == 0 ? acc0 : acc1) + lane_off;
+                const uint32_t acc = acc0 + lane_off;
+                const uint32_t tm_dst = (layer == 0 ? tm_h0 : tm_h1) + lane_off;
 #pragma unroll 1
                 for (int c0 = 0; c0 < FQ_HID; c0 += 32) {
                     uint32_t v[32];
@@ -516,36 +529,46 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     tmem_ld_wait();
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __ldg(bias + c0 + j), 0.f);
+                    for (int q = 0; q < 8; ++q) {          // shared-memory broadcast reads (every lane the same address)
+                        const float4 b4 = bias4[(c0 >> 2) + q];
+                        f[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
+                        f[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
+                        f[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
+                        f[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
+                    }
                     if (layer == 2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dot = fmaf(f[j], __ldg(p.wout + c0 + j), dot);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w4 = wout4[(c0 >> 2) + q];
+                            dot = fmaf(f[4 * q + 0], w4.x, dot);
+                            dot = fmaf(f[4 * q + 1], w4.y, dot);
+                            dot = fmaf(f[4 * q + 2], w4.z, dot);
+                            dot = fmaf(f[4 * q + 3], w4.w, dot);
+                        }
                     }
-                    uint4 packed[4];
+                    uint32_t packed[16];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float g[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) g[j] = f[q * 8 + j];
-                        packed[q] = float8_to_bf16(g);
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        packed[j] = *reinterpret_cast<uint32_t *>(&h);
                     }
-                    if (layer < 2) {
-                        uint8_t *hc = s.h + (c0 >> 6) * FQ_A_BYTES;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<uint4 *>(hc + swz128(r, ((c0 & 63) >> 3) + q)) = packed[q];
-                    }
+                    if (layer < 2) tmem_st16(tm_dst + (c0 >> 1), packed);     // K elements (c0 .. c0+31) -> 16 packed columns
                     if (p.save_h && row_ok && p.points) {
                         __nv_bfloat16 *dst = p.save_h + ((int64_t)layer * p.total + row) * FQ_HID + c0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4 *>(dst + q * 8) = packed[q];
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4 *>(dst + q * 8) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
                     }
                 }
                 if (layer < 2) {
-                    fence_proxy_async();
+                    tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s.h_ready);
+                } else {
+                    tc_fence_before();                  // accumulator reads complete: the next tile's fc_0 may overwrite it
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s.acc_free);
                 }
                 if (threadIdx.x == 0) fq_trace(p, 2, tn, 610 + layer);
             }
@@ -554,7 +577,6 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 if (p.apply_sigmoid) logit = 1.0f / (1.0f + __expf(-logit));
                 p.out[out_idx] = logit;
             }
-            tc_fence_before();
         }
     }
     __syncthreads();
@@ -628,10 +650,14 @@ static int fq_launch(const FqParams &p, int64_t n_tiles, cudaStream_t st) {
     static const int gw = getenv("SVR_FQ_GW") ? atoi(getenv("SVR_FQ_GW")) : 16;     // EXPERIMENT ONLY
     const_cast<FqParams &>(p).debug = getenv("SVR_FQ_DEBUG") ? atoi(getenv("SVR_FQ_DEBUG")) : 0;
     const_cast<FqParams &>(p).trace = g_fq_trace;
+    {
+        int nb = getenv("SVR_FQ_NB") ? atoi(getenv("SVR_FQ_NB")) : FQ_NB;
+        const_cast<FqParams &>(p).nb = nb < 2 ? 2 : (nb > FQ_NB_MAX ? FQ_NB_MAX : nb);
+    }
     if (gw == 8)
-        fused_query_kernel<8><<<grid, fq_threads(8), FQ_SMEM, st>>>(p, n_tiles);
+        fused_query_kernel<8><<<grid, fq_threads(8), fq_smem(p.nb), st>>>(p, n_tiles);
     else
-    fused_query_kernel<16><<<grid, fq_threads(16), FQ_SMEM, st>>>(p, n_tiles);
+        fused_query_kernel<16><<<grid, fq_threads(16), fq_smem(p.nb), st>>>(p, n_tiles);
     SVR_LAUNCH_CHECK();
     return 0;
 }

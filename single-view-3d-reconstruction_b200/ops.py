@@ -820,7 +820,7 @@ class _Query(torch.autograd.Function):
                 _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
                                                  None, coarse_t, None, st), "gather_bwd")
             gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
-        return (None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
+        return (None, None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
 
 
 # =================================================================================================
