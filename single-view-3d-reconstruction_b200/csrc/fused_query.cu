@@ -23,7 +23,6 @@
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tc05.cuh"
-#include <cstdlib>
 
 namespace svr {
 using namespace tc;
@@ -41,7 +40,8 @@ constexpr int FQ_WGEO_BYTES = 512;               // per-level geometry of the wi
 // Shared memory is kept SMALL on purpose: what a CTA does not request stays L1 data cache (228 KB - shared memory per SM),
 // and the gather lives on L1 hits -- neighbouring (spatially sorted) rows and the 7 stencil points of a row read the same
 // voxels.  Staging the corner loads through shared memory (cp.async, one 128-byte slot per thread: latency fully hidden, no
-// registers in flight) was measured SLOWER (1.39 vs 1.02 ms at config 2) because its 64 KB shrink L1 to a few KB.
+// registers in flight) was measured SLOWER (1.39 vs 1.02 ms at config 2) because its 64 KB shrink L1 to a few KB.  A warp
+// that prefetches the next tile's fine-level sectors into L2 (prefetch.global.L2) was also slower (1.08 vs 0.98 ms).
 constexpr int fq_smem(int nb) { return 1024 + FQ_NA * FQ_A_BYTES + nb * FQ_B_BYTES + FQ_BIAS_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4 + FQ_WGEO_BYTES; }
 constexpr int FQ_SMEM = fq_smem(FQ_NB_MAX);
 
@@ -80,7 +80,6 @@ struct FqParams {
     __nv_bfloat16 *save_h;      // optional (3, total, 256)
     __nv_bfloat16 *save_feat;   // optional (total, KP)
     int apply_sigmoid;
-    int debug;                  // EXPERIMENT ONLY: ablation bits
     int nb;                     // weight-ring depth (2..FQ_NB_MAX)
     long long *trace;           // debug: per-role (tag, SM clock) records of block 0 (svr_debug_fq_trace), else null
 };
@@ -309,29 +308,12 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                 const int u = kc * 8 + unit_in_chunk;
                 UnitCtx uc;
                 make_unit_ctx_packed(p.P, s.utab[u], p.vols.v, uc);
-                // compile-time specialised gather for the 128-net's levels (uniform over the chunk's threads per unit)
-                int spec = 0;
-                if (!p.P.align && uc.real && uc.level > 0 && uc.W == uc.H && uc.H == uc.D) {
-                    if (uc.W == 128 && uc.C == 16) spec = 1;
-                    else if (uc.W == 64 && uc.C == 32) spec = 2;
-                    else if (uc.W == 32 && uc.C == 64) spec = 3;
-                    else if (uc.W == 16 && uc.C == 128) spec = 4;
-                    else if (uc.W == 8 && uc.C == 128) spec = 5;
-                }
                 auto gather_one = [&](float qx, float qy, float qz, int scene) -> uint4 {
-                    switch (spec) {
-                        case 1: return gather_unit_fast_c<128, 16>(uc, qx, qy, qz, scene);
-                        case 2: return gather_unit_fast_c<64, 32>(uc, qx, qy, qz, scene);
-                        case 3: return gather_unit_fast_c<32, 64>(uc, qx, qy, qz, scene);
-                        case 4: return gather_unit_fast_c<16, 128>(uc, qx, qy, qz, scene);
-                        case 5: return gather_unit_fast_c<8, 128>(uc, qx, qy, qz, scene);
-                        default: return gather_unit_fast(uc, p.P.align, qx, qy, qz, scene);
-                    }
+                    return gather_unit_bf(uc, p.P.align, qx, qy, qz, scene);
                 };
                 mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
                 if (gt == 0) fq_trace(p, 0, tn, 100 + kc);
                 uint8_t *a_st = s.a + st * FQ_A_BYTES;
-                if (!(p.debug & 4))
 #pragma unroll 2
                 for (int r = gt >> 3; r < FQ_TILE; r += FQ_GATHER_THREADS / 8) {
                     const float4 q = pts_s[r];
@@ -391,7 +373,6 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                         mbar_wait(s.a_empty + st, ((gc / FQ_NA) & 1) ^ 1);
                         if (gt == 0) fq_trace(p, 0, tn, 100 + kc);
                         uint8_t *a_st = s.a + st * FQ_A_BYTES;
-                        if (!(p.debug & 8))
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
                             const int r = (gt >> 3) + j * (FQ_GATHER_THREADS / 8);
@@ -430,10 +411,6 @@ __global__ void __launch_bounds__(fq_threads(FQ_GATHER_WARPS), 1) fused_query_ke
                     const uint8_t *src = c < KC0 ? p.w0_img + (size_t)c * FQ_B_BYTES
                                                  : (c < KC0 + 4 ? p.w1_img + (size_t)(c - KC0) * FQ_B_BYTES
                                                                 : p.w2_img + (size_t)(c - KC0 - 4) * FQ_B_BYTES);
-                    if (p.debug & 2) {
-                        mbar_arrive(s.b_full + st);
-                        continue;
-                    }
                     mbar_arrive_expect_tx(s.b_full + st, FQ_B_BYTES);
                     bulk_g2s(smem_u32(s.b + st * FQ_B_BYTES), src, FQ_B_BYTES, s.b_full + st);
                 }
@@ -641,23 +618,14 @@ static int fq_launch(const FqParams &p, int64_t n_tiles, cudaStream_t st) {
     int dev;
     if (once.needed(dev)) {
         SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
-        SVR_CUDA(cudaFuncSetAttribute(fused_query_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM));
         once.done(dev);
     }
     if (n_tiles <= 0) return 0;
     int grid = sm_count();
     if (n_tiles < grid) grid = (int)n_tiles;
-    static const int gw = getenv("SVR_FQ_GW") ? atoi(getenv("SVR_FQ_GW")) : 16;     // EXPERIMENT ONLY
-    const_cast<FqParams &>(p).debug = getenv("SVR_FQ_DEBUG") ? atoi(getenv("SVR_FQ_DEBUG")) : 0;
     const_cast<FqParams &>(p).trace = g_fq_trace;
-    {
-        int nb = getenv("SVR_FQ_NB") ? atoi(getenv("SVR_FQ_NB")) : FQ_NB;
-        const_cast<FqParams &>(p).nb = nb < 2 ? 2 : (nb > FQ_NB_MAX ? FQ_NB_MAX : nb);
-    }
-    if (gw == 8)
-        fused_query_kernel<8><<<grid, fq_threads(8), fq_smem(p.nb), st>>>(p, n_tiles);
-    else
-        fused_query_kernel<16><<<grid, fq_threads(16), fq_smem(p.nb), st>>>(p, n_tiles);
+    const_cast<FqParams &>(p).nb = FQ_NB;
+    fused_query_kernel<16><<<grid, fq_threads(16), fq_smem(FQ_NB), st>>>(p, n_tiles);
     SVR_LAUNCH_CHECK();
     return 0;
 }

@@ -340,52 +340,32 @@ __device__ __forceinline__ uint4 gather_unit_fast(const UnitCtx &c, int align, f
     }
     return make_uint4(out[0], out[1], out[2], out[3]);
 }
-// gather_unit_fast specialised at compile time for a cubic grid of LW^3 voxels with LC channels and align_corners = False
-// (the five sampled levels of the 128-net): sizes, strides and the 8 corner offsets become immediates, the index
-// products become shifts.  Same arithmetic, same bits.
-template <int LW, int LC>
-__device__ __forceinline__ uint4 gather_unit_fast_c(const UnitCtx &c, float px, float py, float pz, int scene) {
-    constexpr int align = 0;
-    constexpr float fLW = (float)LW;
-    constexpr int cW = LW, cH = LW, cD = LW, cC = LC, c_sy = LW * LC, c_sz = LW * LW * LC;
-    constexpr int64_t c_scene = (int64_t)LW * LW * LW * LC;
-    constexpr bool c_coarse = LW <= 16;
-    // q = 2*p + displacement: 2*p is exact, so the fused form rounds exactly like the reference's mul + add
-    const float ix = unnorm(__fadd_rn(__fmul_rn(2.0f, pz), c.dx), fLW, align);
-    const float iy = unnorm(__fadd_rn(__fmul_rn(2.0f, py), c.dy), fLW, align);
-    const float iz = unnorm(__fadd_rn(__fmul_rn(2.0f, px), c.dz), fLW, align);
-    float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-    fx = fminf(fmaxf(fx, -4.0f), fLW + 2.0f);
-    fy = fminf(fmaxf(fy, -4.0f), fLW + 2.0f);
-    fz = fminf(fmaxf(fz, -4.0f), fLW + 2.0f);
-    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-    const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
-    const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
-    const float wz1 = iz - fz, wz0 = (fz + 1.0f) - iz;
-    const __nv_bfloat16 *ptr = c.base + (int64_t)scene * c_scene + ((z0 * cH + y0) * cW + x0) * cC;
-    const bool interior = x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + 1 < cW && y0 + 1 < cH && z0 + 1 < cD;
+// Branch-free variant used by the fused kernel for the levels that have no halo'd copy: every corner coordinate is clamped
+// into the volume and all 8 loads are issued unconditionally; the weight of an out-of-range corner is forced to zero
+// (fmaf(v, 0, acc) == acc for finite v: the bits of the bounds-checked form), a cell that lies entirely outside gets zero
+// weights.  No divergence between interior and border rows of a warp, and the loads are not serialised behind predicates.
+__device__ __forceinline__ uint4 gather_unit_bf(const UnitCtx &c, int align, float px, float py, float pz, int scene) {
+    const float ix = unnorm(__fadd_rn(__fmul_rn(2.0f, pz), c.dx), c.fw, align);
+    const float iy = unnorm(__fadd_rn(__fmul_rn(2.0f, py), c.dy), c.fh, align);
+    const float iz = unnorm(__fadd_rn(__fmul_rn(2.0f, px), c.dz), c.fd, align);
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const bool cell_in = fx >= -1.0f && fx <= c.fw - 1.0f && fy >= -1.0f && fy <= c.fh - 1.0f && fz >= -1.0f && fz <= c.fd - 1.0f;
+    const int x0 = (int)fminf(fmaxf(fx, -1.0f), c.fw - 1.0f), y0 = (int)fminf(fmaxf(fy, -1.0f), c.fh - 1.0f),
+              z0 = (int)fminf(fmaxf(fz, -1.0f), c.fd - 1.0f);
+    const float wx[2] = {x0 >= 0 ? (fx + 1.0f) - ix : 0.f, x0 + 1 < c.W ? ix - fx : 0.f};
+    const float wy[2] = {y0 >= 0 ? (fy + 1.0f) - iy : 0.f, y0 + 1 < c.H ? iy - fy : 0.f};
+    const float wz[2] = {(cell_in && z0 >= 0) ? (fz + 1.0f) - iz : 0.f, (cell_in && z0 + 1 < c.D) ? iz - fz : 0.f};
+    const int ox[2] = {max(x0, 0) * c.C, min(x0 + 1, c.W - 1) * c.C};
+    const int oy[2] = {max(y0, 0) * c.sy, min(y0 + 1, c.H - 1) * c.sy};
+    const int oz[2] = {max(z0, 0) * c.sz, min(z0 + 1, c.D - 1) * c.sz};
+    const __nv_bfloat16 *base = c.base + (int64_t)scene * c.scene_stride;
+    const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
     uint4 raw[8];
     float w[8];
-    const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
-    if (interior && !c_coarse) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int off = ((k & 1) ? cC : 0) + ((k & 2) ? c_sy : 0) + ((k & 4) ? c_sz : 0);
-            raw[k] = __ldg(reinterpret_cast<const uint4 *>(ptr + off));
-            w[k] = wxy[k & 3] * ((k & 4) ? wz1 : wz0);
-        }
-    } else {
-#pragma unroll
-        const bool vx[2] = {(unsigned)x0 < (unsigned)cW, (unsigned)(x0 + 1) < (unsigned)cW};
-        const bool vy[2] = {(unsigned)y0 < (unsigned)cH, (unsigned)(y0 + 1) < (unsigned)cH};
-        const bool vz[2] = {(unsigned)z0 < (unsigned)cD, (unsigned)(z0 + 1) < (unsigned)cD};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const bool in = vx[k & 1] && vy[(k >> 1) & 1] && vz[k >> 2];
-            const int off = ((k & 1) ? cC : 0) + ((k & 2) ? c_sy : 0) + ((k & 4) ? c_sz : 0);
-            raw[k] = in ? __ldg(reinterpret_cast<const uint4 *>(ptr + off)) : make_uint4(0, 0, 0, 0);
-            w[k] = in ? wxy[k & 3] * ((k & 4) ? wz1 : wz0) : 0.f;
-        }
+    for (int k = 0; k < 8; ++k) {
+        raw[k] = __ldg(reinterpret_cast<const uint4 *>(base + (oz[k >> 2] + oy[(k >> 1) & 1] + ox[k & 1])));
+        w[k] = wxy[k & 3] * wz[k >> 2];
     }
     unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
