@@ -104,7 +104,7 @@ _lib = None
 
 # kernels launched per entry point (memsets are not kernels of ours and are not counted)
 KERNELS_PER_CALL = {
-    "svr_unproject_fwd": 1, "svr_unproject_bwd": 1, "svr_norm_grid_space": 1, "svr_voxelize_fwd": 7, "svr_voxelize_bwd": 1,
+    "svr_unproject_fwd": 1, "svr_unproject_bwd": 1, "svr_norm_grid_space": 1, "svr_voxelize_fwd": 9, "svr_voxelize_bwd": 1,
     "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_pack_volume_halo": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
     "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 1, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
     "svr_decoder_head_bwd": 2, "svr_colsum_bf16": 2, "svr_query_fwd_fused": 1, "svr_dense_eval": 1, "svr_decoder_bwd_fused": 1, "svr_pack_decoder_image": 1, "svr_sort_points": 4, "svr_bias_relu_cl": 1, "svr_widen_bf16": 1, "svr_relu_bwd_cl": 2, "svr_conv1_relu_fwd": 1, "svr_conv1_relu_bwd": 2, "svr_conv1_relu_bn_stats": 2, "svr_conv1_relu_bn_apply": 1, "svr_conv1_relu_bn_bwd": 4, "svr_maxpool2_cl_fwd": 1, "svr_maxpool2_cl_bwd": 1,

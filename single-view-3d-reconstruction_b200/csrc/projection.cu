@@ -121,51 +121,91 @@ __global__ void vox_mark_kernel(const float *__restrict__ pts, VoxParams vp, int
     cell_of_point[i] = cell;
 }
 
-// exclusive scan of one map's array by one CTA (1024 threads); MODE 0: popcount of words, 1: ints
+// Exclusive scan of every map's array, two launches, both grid-wide (round 1 used ONE CTA per map: 64 CTAs on 148 SMs
+// walking up to 512 chunks each).  MODE 0: popcount of bitmap words, MODE 1: ints.  A block owns SCAN_BLOCK consecutive
+// entries of one map; n_dynamic (nullable) holds the per-map number of valid entries.
+constexpr int SCAN_BLOCK = 4096, SCAN_THREADS = 256, SCAN_PER_THREAD = SCAN_BLOCK / SCAN_THREADS;
+
 template <int MODE>
-__global__ void __launch_bounds__(1024) scan_per_map_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                                                            int n_static, const int *__restrict__ n_dynamic,
-                                                            int stride, int *__restrict__ total_out) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s, chunk_total_s;
-    const int b = blockIdx.x;
+__device__ __forceinline__ uint32_t scan_load(const uint32_t *__restrict__ src, int i, int n) {
+    if (i >= n) return 0u;
+    return MODE == 0 ? (uint32_t)__popc(src[i]) : src[i];
+}
+
+// launch 1: per-block totals
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t *__restrict__ in, int n_static,
+                                                                        const int *__restrict__ n_dynamic, int stride, int nblk,
+                                                                        uint32_t *__restrict__ bsum) {
+    __shared__ uint32_t red[SCAN_THREADS / 32];
+    const int b = blockIdx.x / nblk, j = blockIdx.x - b * nblk;
     const int n = n_dynamic ? n_dynamic[b] : n_static;
     const uint32_t *src = in + (size_t)b * stride;
-    uint32_t *dst = out + (size_t)b * stride;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    uint32_t v = 0;
+    const int i0 = j * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) v += scan_load<MODE>(src, i0 + k, n);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        int i = base + threadIdx.x;
-        uint32_t v = 0;
-        if (i < n) v = MODE == 0 ? (uint32_t)__popc(src[i]) : src[i];
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-            uint32_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_sums[lane] = wi - w;  // exclusive prefix of the warp totals
-            if (lane == 31) chunk_total_s = wi;
-        }
-        __syncthreads();
-        uint32_t excl = carry_s + warp_sums[warp] + incl - v;
-        if (i < n) dst[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += chunk_total_s;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += red[w];
+        bsum[blockIdx.x] = t;
     }
-    if (threadIdx.x == 0 && total_out) total_out[b] = (int)carry_s;
+}
+
+// launch 2: block prefix (sum of the map's earlier block totals) + local exclusive scan; the map total goes to total_out
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int n_static,
+                                                                    const int *__restrict__ n_dynamic, int stride, int nblk,
+                                                                    const uint32_t *__restrict__ bsum, int *__restrict__ total_out) {
+    __shared__ uint32_t red[SCAN_THREADS / 32];
+    __shared__ uint32_t base_s;
+    const int b = blockIdx.x / nblk, j = blockIdx.x - b * nblk;
+    const int n = n_dynamic ? n_dynamic[b] : n_static;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // prefix of the earlier blocks of this map (nblk is small: <= 128 for a 256^3 bitmap)
+    uint32_t pre = 0;
+    for (int k = threadIdx.x; k < j; k += SCAN_THREADS) pre += bsum[b * nblk + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if (lane == 0) red[warp] = pre;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += red[w];
+        base_s = t;
+    }
+    __syncthreads();
+    const uint32_t *src = in + (size_t)b * stride;
+    uint32_t *dst = out + (size_t)b * stride;
+    const int i0 = j * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        v[k] = scan_load<MODE>(src, i0 + k, n);
+        tsum += v[k];
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();          // red is reused
+    if (lane == 31) red[warp] = incl;
+    __syncthreads();
+    uint32_t wpre = 0;
+    for (int w = 0; w < warp; ++w) wpre += red[w];
+    uint32_t run = base_s + wpre + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        if (i0 + k < n) dst[i0 + k] = run;
+        run += v[k];
+    }
+    if (total_out && j == nblk - 1 && threadIdx.x == SCAN_THREADS - 1) total_out[b] = (int)run;
 }
 
 __device__ __forceinline__ int cell_rank(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wprefix,
@@ -174,10 +214,10 @@ __device__ __forceinline__ int cell_rank(const uint32_t *__restrict__ bitmap, co
     return (int)(wprefix[cell >> 5] + __popc(w & ((1u << (cell & 31)) - 1u)));
 }
 
-// K3: compact id per point, per-cell counts, linear index per compact id
+// K3: compact id per point (the rank of its cell among the map's occupied cells), per-cell counts
 __global__ void vox_count_kernel(VoxParams vp, const int *__restrict__ cell_of_point, const uint32_t *__restrict__ bitmap,
                                  const uint32_t *__restrict__ wprefix, int *__restrict__ cid_of_point,
-                                 int *__restrict__ count, int *__restrict__ cell_lin) {
+                                 int *__restrict__ count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)vp.B * vp.N) return;
     int b = (int)(i / vp.N);
@@ -186,7 +226,6 @@ __global__ void vox_count_kernel(VoxParams vp, const int *__restrict__ cell_of_p
     if (cell >= 0) {
         id = cell_rank(bitmap + (size_t)b * vp.Wd, wprefix + (size_t)b * vp.Wd, cell);
         atomicAdd(count + (size_t)b * vp.N + id, 1);
-        cell_lin[(size_t)b * vp.N + id] = cell;  // every writer stores the same value
     }
     cid_of_point[i] = id;
 }
@@ -204,10 +243,12 @@ __global__ void vox_fill_kernel(VoxParams vp, const int *__restrict__ cid_of_poi
     order[o + slot] = n;
 }
 
-// K6: rank every point inside its cell by point index (counting smaller indices) -> deterministic
-__global__ void vox_rank_kernel(VoxParams vp, const int *__restrict__ cid_of_point, const int *__restrict__ start,
-                                const int *__restrict__ count, const int *__restrict__ order,
-                                int *__restrict__ sorted) {
+// K6: rank every point inside its cell by point index (counting smaller indices) -> deterministic; the point's
+// fractional coordinates (the only per-point data the accumulation needs) are stored at its final slot, so that a cell's
+// contributions are one contiguous run of 16-byte records in reference (point index) order
+__global__ void vox_rank_kernel(const float *__restrict__ pts, VoxParams vp, const int *__restrict__ cid_of_point,
+                                const int *__restrict__ start, const int *__restrict__ count, const int *__restrict__ order,
+                                float4 *__restrict__ rec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)vp.B * vp.N) return;
     int b = (int)(i / vp.N), n = (int)(i % vp.N);
@@ -217,71 +258,112 @@ __global__ void vox_rank_kernel(VoxParams vp, const int *__restrict__ cid_of_poi
     int s = start[o + id], c = count[o + id];
     int rank = 0;
     for (int t = 0; t < c; ++t) rank += (order[o + s + t] < n);
-    sorted[o + s + rank] = n;
+    int f[3];
+    float r[3], m[3];
+    point_frac(pts + i * 3, vp, f, r, m);
+    rec[o + s + rank] = make_float4(r[0], r[1], r[2], 0.f);
 }
 
-// K7: one thread per (occupied cell, corner shift) candidate; the owner of the target voxel sums
-// all contributions in reference order and writes the voxel.
-__global__ void vox_accumulate_kernel(const float *__restrict__ pts, VoxParams vp, const int *__restrict__ ucount,
-                                      const int *__restrict__ cell_lin, const uint32_t *__restrict__ bitmap,
-                                      const uint32_t *__restrict__ wprefix, const int *__restrict__ start,
-                                      const int *__restrict__ count, const int *__restrict__ sorted,
-                                      int64_t tail_start, float *__restrict__ grid, uint32_t *__restrict__ sat_mask) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)vp.B * vp.N * 8) return;
-    int shift = (int)(t & 7);
-    int64_t cu = t >> 3;
-    int b = (int)(cu / vp.N), u = (int)(cu % vp.N);
-    if (u >= ucount[b]) return;
-    const size_t o = (size_t)b * vp.N;
+// K7: DENSE pass -- every voxel of the grid is written exactly once, by this kernel (no memset, no scattered writes).
+// A warp owns 1024 consecutive voxels of one map (32 bitmap words).  Voxel v receives pass ps (projection.py:75-78, corner
+// shift (k,j,i)) from the cell v - off(ps), off = (k*S1 + j)*S2 + i in linear cell numbering; cells on the upper faces are
+// never occupied (a cell needs f+1 < S), so the wrap-around of the linear offset at row / slab ends can only hit empty
+// cells and needs no coordinate test.  Lane l computes the 8 "pass ps contributes" masks of word l with funnel shifts of the
+// bitmap; then, word by word, the masks are broadcast, lane l takes voxel l of the word, and the lanes whose voxel is
+// touched walk the (at most 8) source cells in pass order and their records in point order -- the reference's serial
+// accumulation order, non-contracted fp32 adds -- followed by the 8-fold self-sum and the clamp.  Untouched voxels get 0.
+__device__ __forceinline__ uint32_t bitmap_window(const uint32_t *__restrict__ bm, int64_t bit0, int64_t nbits) {
+    // 32 bits of the bitmap starting at bit index bit0 (may be negative or run past the end: zeros there)
+    if (bit0 <= -32 || bit0 >= nbits) return 0u;
+    const int64_t w0 = bit0 >> 5;          // floor division (arithmetic shift)
+    const int sh = (int)(bit0 & 31);
+    const int64_t nw = (nbits + 31) >> 5;
+    const uint32_t lo = (w0 >= 0 && w0 < nw) ? bm[w0] : 0u;
+    const uint32_t hi = (sh && w0 + 1 >= 0 && w0 + 1 < nw) ? bm[w0 + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__global__ void __launch_bounds__(256) vox_dense_kernel(VoxParams vp, const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ wprefix,
+                                                        const int *__restrict__ start, const int *__restrict__ count,
+                                                        const float4 *__restrict__ rec, int64_t tail_start, int spans_per_map,
+                                                        float *__restrict__ grid, uint32_t *__restrict__ sat_mask) {
+    __shared__ __align__(16) float out_s[8][1024];      // one 4 KB span per warp, assembled here and written out coalesced
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int b = (int)(wid / spans_per_map);
+    if (b >= vp.B) return;
+    const int span = (int)(wid - (int64_t)b * spans_per_map);
     const uint32_t *bm = bitmap + (size_t)b * vp.Wd;
     const uint32_t *wp = wprefix + (size_t)b * vp.Wd;
-    int cell = cell_lin[o + u];
-    int cz = cell / (vp.S[1] * vp.S[2]);
-    int cy = (cell / vp.S[2]) % vp.S[1];
-    int cx = cell % vp.S[2];
-    int vz = cz + ((shift >> 2) & 1), vy = cy + ((shift >> 1) & 1), vx = cx + (shift & 1);
-    // source cell of every pass for this voxel, and ownership: the first pass with an occupied cell
-    int src_id[8];
-    bool owner = true;
+    const size_t o = (size_t)b * vp.N;
+    const int64_t vbase = (int64_t)span * 1024;
+    const int64_t v_word0 = vbase + (int64_t)lane * 32;     // first voxel of this lane's word
+    const int s12 = vp.S[1] * vp.S[2];
+    int off[8];
+    uint32_t m[8];
+    uint32_t t = 0;
 #pragma unroll
     for (int ps = 0; ps < 8; ++ps) {
-        int sz = vz - ((ps >> 2) & 1), sy = vy - ((ps >> 1) & 1), sx = vx - (ps & 1);
-        int id = -1;
-        if (sz >= 0 && sy >= 0 && sx >= 0 && sz < vp.S[0] && sy < vp.S[1] && sx < vp.S[2]) {
-            int c = (sz * vp.S[1] + sy) * vp.S[2] + sx;
-            if ((bm[c >> 5] >> (c & 31)) & 1u) id = cell_rank(bm, wp, c);
-        }
-        src_id[ps] = id;
-        if (ps < shift && id >= 0) owner = false;
+        off[ps] = ((ps >> 2) & 1) * s12 + ((ps >> 1) & 1) * vp.S[2] + (ps & 1);
+        m[ps] = bitmap_window(bm, v_word0 - off[ps], vp.V);
+        t |= m[ps];
     }
-    if (!owner) return;
-    float acc = 0.f;
+    float *gmap = grid + (int64_t)b * vp.V;
+    const bool vec_ok = vbase + 1024 <= vp.V && (((uintptr_t)(gmap + vbase)) & 15) == 0;
+    if (!__any_sync(0xffffffffu, t != 0)) {            // untouched span: 4 KB of zeros, 16-byte stores
+        if (vec_ok) {
 #pragma unroll
-    for (int ps = 0; ps < 8; ++ps) {
-        int id = src_id[ps];
-        if (id < 0) continue;
-        int s = start[o + id], c = count[o + id];
-        for (int q = 0; q < c; ++q) {
-            int n = sorted[o + s + q];
-            int f[3];
-            float r[3], m[3];
-            point_frac(pts + (o + n) * 3, vp, f, r, m);
-            acc = __fadd_rn(acc, corner_weight(r, m, ps));
+            for (int k = 0; k < 8; ++k) reinterpret_cast<float4 *>(gmap + vbase)[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int k = 0; k < 32; ++k)
+                if (vbase + k * 32 + lane < vp.V) gmap[vbase + k * 32 + lane] = 0.f;
         }
+        return;
     }
-    int64_t flat = (int64_t)b * vp.V + ((int64_t)vz * vp.S[1] + vy) * vp.S[2] + vx;
-    float s8;
-    if (flat < tail_start) {  // torch.stack(8 aliases).sum(0): row-after-row accumulation
-        s8 = acc;
+    float *mine = out_s[wib] + lane * 32;
 #pragma unroll
-        for (int q = 0; q < 7; ++q) s8 = __fadd_rn(s8, acc);
-    } else {                  // ATen row_sum remainder path: 4 interleaved partial sums
-        float p2 = __fadd_rn(acc, acc);
-        s8 = __fadd_rn(__fadd_rn(__fadd_rn(p2, p2), p2), p2);
+    for (int k = 0; k < 8; ++k) reinterpret_cast<float4 *>(mine)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // every lane walks the touched voxels of ITS word: the lanes' accumulation chains run side by side
+    while (t) {
+        const int bit = __ffs((int)t) - 1;
+        t &= t - 1;
+        const int64_t v = v_word0 + bit;
+        float acc = 0.f;
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+            if (!((m[ps] >> bit) & 1u)) continue;
+            const int c = (int)(v - off[ps]);
+            const int id = cell_rank(bm, wp, c);
+            const int s0 = start[o + id], cnt = count[o + id];
+            for (int q = 0; q < cnt; ++q) {
+                const float4 rr = __ldg(rec + o + s0 + q);
+                const float r[3] = {rr.x, rr.y, rr.z};
+                const float mm[3] = {__fsub_rn(1.0f, rr.x), __fsub_rn(1.0f, rr.y), __fsub_rn(1.0f, rr.z)};
+                acc = __fadd_rn(acc, corner_weight(r, mm, ps));
+            }
+        }
+        const int64_t flat = (int64_t)b * vp.V + v;
+        float s8;
+        if (flat < tail_start) {  // torch.stack(8 aliases).sum(0): row-after-row accumulation
+            s8 = acc;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) s8 = __fadd_rn(s8, acc);
+        } else {                  // ATen row_sum remainder path: 4 interleaved partial sums
+            const float p2 = __fadd_rn(acc, acc);
+            s8 = __fadd_rn(__fadd_rn(__fadd_rn(p2, p2), p2), p2);
+        }
+        if (sat_mask && s8 > 1.0f) atomicOr(sat_mask + (flat >> 5), 1u << (flat & 31));
+        mine[bit] = s8 < 0.f ? 0.f : (s8 > 1.f ? 1.f : s8);
     }
-    if (sat_mask && s8 > 1.0f) atomicOr(sat_mask + (flat >> 5), 1u << (flat & 31));
-    grid[flat] = s8 < 0.f ? 0.f : (s8 > 1.f ? 1.f : s8);
+    __syncwarp();
+    if (vec_ok) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            reinterpret_cast<float4 *>(gmap + vbase)[k * 32 + lane] = reinterpret_cast<const float4 *>(out_s[wib])[k * 32 + lane];
+    } else {
+        for (int k = 0; k < 32; ++k)
+            if (vbase + k * 32 + lane < vp.V) gmap[vbase + k * 32 + lane] = out_s[wib][k * 32 + lane];
+    }
 }
 
 __global__ void vox_bwd_kernel(const float *__restrict__ pts, const float *__restrict__ ggrid,
@@ -642,8 +724,9 @@ static int fill_vox(VoxParams &vp, int B, int N, const int64_t *dims3, double ep
 }
 
 struct VoxWorkspace {
-    int *cell_of_point, *cid_of_point, *cell_lin, *count, *start, *cursor, *order, *sorted, *ucount;
-    uint32_t *bitmap, *wprefix;
+    int *cell_of_point, *cid_of_point, *count, *start, *cursor, *order, *ucount;
+    float4 *rec;
+    uint32_t *bitmap, *wprefix, *bsum;
     size_t bytes, zero_bytes;   // [bitmap | count | cursor] are contiguous and zero-filled per call
 };
 
@@ -662,11 +745,12 @@ static void layout_ws(VoxWorkspace &w, char *base, int B, int N, int Wd) {
     w.wprefix = (uint32_t *)take(bw);
     w.cell_of_point = (int *)take(bn);
     w.cid_of_point = (int *)take(bn);
-    w.cell_lin = (int *)take(bn);
     w.start = (int *)take(bn);
     w.order = (int *)take(bn);
-    w.sorted = (int *)take(bn);
+    w.rec = (float4 *)take(bn * 4);
     w.ucount = (int *)take((size_t)B);
+    const size_t nblk = (size_t)(((Wd > N ? Wd : N) + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    w.bsum = (uint32_t *)take((size_t)B * nblk);
     w.bytes = (size_t)(base - origin);
 }
 
@@ -730,11 +814,14 @@ int svr_voxelize_fwd(const float *pts, int B, int N, const int64_t *dims3_host, 
     int64_t total_vox = (int64_t)B * vp.V;
     if (tail_start < 0 || tail_start > total_vox) tail_start = total_vox;
     if (total_vox == 0) return 0;
-    SVR_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), st));
     if (sat_mask) SVR_CUDA(cudaMemsetAsync(sat_mask, 0, (size_t)((total_vox + 31) / 32) * 4, st));
-    if (N == 0) return 0;
+    if (N == 0) {
+        SVR_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), st));
+        return 0;
+    }
     SVR_REQUIRE(pts && workspace, "voxelize: null pointer");
     SVR_REQUIRE(((uintptr_t)workspace & 255) == 0, "voxelize: workspace must be 256-byte aligned");
+    SVR_REQUIRE(vp.V < ((int64_t)1 << 31), "voxelize: more than 2^31 voxels per map");
     VoxWorkspace w;
     layout_ws(w, (char *)workspace, B, N, vp.Wd);
     SVR_REQUIRE(workspace_bytes >= w.bytes, "voxelize: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
@@ -743,18 +830,24 @@ int svr_voxelize_fwd(const float *pts, int B, int N, const int64_t *dims3_host, 
     const unsigned gp = (unsigned)ceil_div<int64_t>(bn, 256);
     vox_mark_kernel<<<gp, 256, 0, st>>>(pts, vp, w.cell_of_point, w.bitmap);
     SVR_LAUNCH_CHECK();
-    scan_per_map_kernel<0><<<B, 1024, 0, st>>>(w.bitmap, w.wprefix, vp.Wd, nullptr, vp.Wd, w.ucount);
+    const int nblk_w = ceil_div(vp.Wd, SCAN_BLOCK), nblk_n = ceil_div(N, SCAN_BLOCK);
+    scan_block_sums_kernel<0><<<(unsigned)(B * nblk_w), SCAN_THREADS, 0, st>>>(w.bitmap, vp.Wd, nullptr, vp.Wd, nblk_w, w.bsum);
+    scan_blocks_kernel<0><<<(unsigned)(B * nblk_w), SCAN_THREADS, 0, st>>>(w.bitmap, w.wprefix, vp.Wd, nullptr, vp.Wd, nblk_w, w.bsum, w.ucount);
     SVR_LAUNCH_CHECK();
-    vox_count_kernel<<<gp, 256, 0, st>>>(vp, w.cell_of_point, w.bitmap, w.wprefix, w.cid_of_point, w.count, w.cell_lin);
+    vox_count_kernel<<<gp, 256, 0, st>>>(vp, w.cell_of_point, w.bitmap, w.wprefix, w.cid_of_point, w.count);
     SVR_LAUNCH_CHECK();
-    scan_per_map_kernel<1><<<B, 1024, 0, st>>>((const uint32_t *)w.count, (uint32_t *)w.start, N, w.ucount, N, nullptr);
+    scan_block_sums_kernel<1><<<(unsigned)(B * nblk_n), SCAN_THREADS, 0, st>>>((const uint32_t *)w.count, N, w.ucount, N, nblk_n, w.bsum);
+    scan_blocks_kernel<1><<<(unsigned)(B * nblk_n), SCAN_THREADS, 0, st>>>((const uint32_t *)w.count, (uint32_t *)w.start, N, w.ucount, N, nblk_n,
+                                                                          w.bsum, nullptr);
     SVR_LAUNCH_CHECK();
     vox_fill_kernel<<<gp, 256, 0, st>>>(vp, w.cid_of_point, w.start, w.cursor, w.order);
     SVR_LAUNCH_CHECK();
-    vox_rank_kernel<<<gp, 256, 0, st>>>(vp, w.cid_of_point, w.start, w.count, w.order, w.sorted);
+    vox_rank_kernel<<<gp, 256, 0, st>>>(pts, vp, w.cid_of_point, w.start, w.count, w.order, w.rec);
     SVR_LAUNCH_CHECK();
-    vox_accumulate_kernel<<<(unsigned)ceil_div<int64_t>(bn * 8, 256), 256, 0, st>>>(
-        pts, vp, w.ucount, w.cell_lin, w.bitmap, w.wprefix, w.start, w.count, w.sorted, tail_start, grid, sat_mask);
+    const int spans = (int)ceil_div<int64_t>(vp.V, 1024);
+    const int64_t warps = (int64_t)B * spans;
+    vox_dense_kernel<<<(unsigned)ceil_div<int64_t>(warps * 32, 256), 256, 0, st>>>(vp, w.bitmap, w.wprefix, w.start, w.count, w.rec, tail_start, spans,
+                                                                                grid, sat_mask);
     SVR_LAUNCH_CHECK();
     return 0;
 }
