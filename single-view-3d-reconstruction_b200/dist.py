@@ -28,6 +28,20 @@ DEFAULT_BUCKETS: Tuple[Tuple[str, ...], ...] = (
 )
 
 
+def _view_like(flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+    """View of flat[off : off + p.numel()] with p's shape AND p's (dense, possibly permuted) strides."""
+    n = p.numel()
+    order = sorted(range(p.dim()), key=lambda d: (-p.stride(d), d))
+    expect, dense = 1, True
+    for d in reversed(order):
+        if p.shape[d] != 1 and p.stride(d) != expect:
+            dense = False
+        expect *= p.shape[d]
+    if not dense:
+        return flat[off:off + n].view(p.shape)
+    return flat.as_strided(p.shape, p.stride(), flat.storage_offset() + off)     # literally the parameter's strides
+
+
 class _Bucket:
     def __init__(self, params: List[torch.nn.Parameter]):
         self.params = params
@@ -37,7 +51,9 @@ class _Bucket:
         self.flat = torch.zeros((n,), device=dev, dtype=dt)
         self.views, off = [], 0
         for p in params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            # same strides as the parameter (the encoder's weights are channels_last_3d): fused optimisers require the
+            # gradient's layout to match the parameter's
+            self.views.append(_view_like(self.flat, off, p))
             off += p.numel()
         self.fired = set()
         self.work = None
@@ -83,7 +99,7 @@ class GradReducer:
         for p, g, v in zip(b.params, grads, b.views):
             if g is not None and g.data_ptr() != v.data_ptr():
                 dst_l.append(v)
-                src_l.append(g.reshape(v.shape) if g.shape != v.shape else g)
+                src_l.append(g)
         if dst_l:
             torch._foreach_copy_(dst_l, src_l)
         if self.weight is not None:

@@ -59,6 +59,12 @@ def _worker(rank, world, port, out_dir):
         red.allreduce()
     torch.cuda.synchronize()
     torch.save({n: p.grad.detach().cpu().clone() for n, p in net.named_parameters()}, Path(out_dir) / f"g{rank}.pt")
+    # the reduced gradients (views of the bucket buffers) must be usable by a fused optimiser: same strides as the
+    # (channels-last) parameters
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+    assert all(p.grad.stride() == p.stride() for p in net.parameters())
+    opt.step()
+    torch.cuda.synchronize()
     # dense evaluation sharded by first-axis slab
     net.eval()
     lattice = (32, 24, 16)
