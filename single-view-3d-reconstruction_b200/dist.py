@@ -49,11 +49,12 @@ class _Bucket:
         n = sum(p.numel() for p in params)
         dev, dt = params[0].device, params[0].dtype
         self.flat = torch.zeros((n,), device=dev, dtype=dt)
-        self.views, off = [], 0
+        self.views, self.offsets, off = [], [], 0
         for p in params:
             # same strides as the parameter (the encoder's weights are channels_last_3d): fused optimisers require the
             # gradient's layout to match the parameter's
             self.views.append(_view_like(self.flat, off, p))
+            self.offsets.append(off)
             off += p.numel()
         self.fired = set()
         self.work = None
@@ -92,6 +93,9 @@ class GradReducer:
 
     # -- bucket helpers ---------------------------------------------------------------------------
     def _launch(self, b: _Bucket):
+        for i, p in enumerate(b.params):      # a module may change its parameters' memory format after construction
+            if b.views[i].stride() != p.stride():      # (the encoder converts itself to channels_last_3d on first use)
+                b.views[i] = _view_like(b.flat, b.offsets[i], p)
         grads = [p.grad for p in b.params]
         if any(g is None for g in grads):      # parameters without a gradient contribute zeros (every rank still
             b.flat.zero_()                     # runs the collective, so the replicas must agree on which they are)
