@@ -50,8 +50,8 @@ def _worker(rank, world, port, out_dir):
     svr_b200.configure(net_res=128, precision=16)
     net = svr_b200.IFNet().to(dev).train()
     net.load_state_dict(R.synthetic_state_dict(61, 128), strict=False)
-    red = svr_dist.GradReducer(net)
-    assert len(red.buckets) >= 3
+    red = svr_dist.GradReducer(net, buckets=svr_dist.FINE_BUCKETS)      # four buckets: every hook-launched path is exercised
+    assert len(red.buckets) == 4
     x, pts, occ = _inputs()
     b, e = svr_dist.shard_range(4, rank, world)
     for _ in range(2):       # two steps: bucket state must reset, p.grad views are replaced by fresh gradients
@@ -65,8 +65,9 @@ def _worker(rank, world, port, out_dir):
     assert all(p.grad.stride() == p.stride() for p in net.parameters())
     opt.step()
     torch.cuda.synchronize()
-    # dense evaluation sharded by first-axis slab
-    net.eval()
+    # dense evaluation sharded by first-axis slab (a fresh module: the training steps above moved the BatchNorm statistics)
+    net = svr_b200.IFNet().to(dev).eval()
+    net.load_state_dict(R.synthetic_state_dict(61, 128), strict=False)
     lattice = (32, 24, 16)
     xb, xe = svr_dist.shard_range(lattice[0] // 8, rank, world)
     slab = net.evaluate_grid(x[:1].to(dev), lattice, scenes=[0], x_range=(xb * 8, xe * 8))
