@@ -41,7 +41,9 @@ constexpr int FQ_WGEO_BYTES = 512;               // per-level geometry of the wi
 // and the gather lives on L1 hits -- neighbouring (spatially sorted) rows and the 7 stencil points of a row read the same
 // voxels.  Staging the corner loads through shared memory (cp.async, one 128-byte slot per thread: latency fully hidden, no
 // registers in flight) was measured SLOWER (1.39 vs 1.02 ms at config 2) because its 64 KB shrink L1 to a few KB.  A warp
-// that prefetches the next tile's fine-level sectors into L2 (prefetch.global.L2) was also slower (1.08 vs 0.98 ms).
+// that prefetches the next tile's fine-level sectors into L2 (prefetch.global.L2) was also slower (1.08 vs 0.98 ms), and so
+// were fp32 halo'd copies of the wide levels (the blend then needs no bf16 unpacking -- 46 instead of 110 instructions per
+// unit -- but reads twice the bytes through L1: 1.54 vs 1.08 ms).
 constexpr int fq_smem(int nb) { return 1024 + FQ_NA * FQ_A_BYTES + nb * FQ_B_BYTES + FQ_BIAS_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4 + FQ_WGEO_BYTES; }
 constexpr int FQ_SMEM = fq_smem(FQ_NB_MAX);
 
