@@ -337,9 +337,10 @@ def query_rooflines(kms, peaks, M, n_scenes, training=True):
             calls, ms = kms[key]
             out.append(_roof(key, ms, calls, *a, **k))
 
-    add("svr_query_fwd_fused", "tensor", fwd_flops, peaks, "fused_query_kernel",
-        f"fused gather + fc_0..fc_out; compulsory HBM bytes {vols_bf16 + x_bytes + 16 * M} (bf16 volumes + grid + 16 B/point)")
-    add("svr_dense_eval", "tensor", fwd_flops, peaks, "fused_query_kernel")
+    add("svr_query_fwd_fused", "tensor", fwd_flops, peaks, "fused_query_kernel" if training else None,
+        f"fused gather + fc_0..fc_out; compulsory HBM bytes {vols_bf16 + x_bytes + 16 * M} (bf16 volumes + grid + 16 B/point)"
+        + ("; traffic = the training launch, which also streams the saved features / activations" if training else ""))
+    add("svr_dense_eval", "tensor", fwd_flops, peaks, None, "same kernel as svr_query_fwd_fused in lattice mode (nothing saved); no ncu capture of this launch")
     add("svr_decoder_bwd_fused", "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "fused_bwd_kernel", "dz1, dz0, dfeat in one kernel")
     if "svr_gemm_tn" in kms:
         calls, ms = kms["svr_gemm_tn"]
