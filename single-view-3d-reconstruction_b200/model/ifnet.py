@@ -281,18 +281,26 @@ class IFNet(nn.Module):
         self.actvn = nn.ReLU()
         self._packed = ops.PackedDecoder()
 
-    def query(self, x, vols, points):
+    def query(self, x, vols, points, prefetched=None):
         """Hot path given precomputed volumes: stencil sampling + decoder -> logits (B,N)."""
         pyr = self.ifnet_feature_extractor.pyramid(x, vols)
+        self.__dict__["_pyr_hint"] = (tuple(x.shape), pyr)
         return ops.query(pyr, self._packed, points, x, self.fc_0.weight, self.fc_0.bias, self.fc_1.weight, self.fc_1.bias,
-                         self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, vols, precision=_precision())
+                         self.fc_2.weight, self.fc_2.bias, self.fc_out.weight, self.fc_out.bias, vols, precision=_precision(),
+                         prefetched=prefetched)
 
     def encode(self, x):
         """The encoder's sampled volumes (in the fp32 tier cuDNN's TF32 convolutions are off, see ``_apply_precision``)."""
         return self.ifnet_feature_extractor.encode(x)
 
     def forward(self, x, points):
-        return self.query(x, self.encode(x), points)
+        # the point sort and the decoder-weight packing do not depend on the encoder: issue them on a side stream first
+        # (the pyramid of this input shape is known from the previous call)
+        pf, hint = None, self.__dict__.get("_pyr_hint")
+        if (ops.OVERLAP_PREP and hint is not None and hint[0] == tuple(x.shape) and x.is_cuda and points.is_cuda and points.shape[0] * points.shape[1] > 0
+                and _precision() != 32 and self.fused_available() and not self._packed.frozen):
+            pf = ops.QueryPrefetch(hint[1], self._packed, points, self.fc_0.weight, self.fc_1.weight, self.fc_2.weight)
+        return self.query(x, self.encode(x), points, prefetched=pf)
 
     def fused_available(self) -> bool:
         return self.fc_0.out_channels == 256 and self.fc_1.out_channels == 256 and self.fc_2.out_channels == 256

@@ -612,6 +612,16 @@ def _gemm_tn(A, B, M, N, P, out, accumulate=False):
 
 
 RELU, ST_BF16, ST_F32, MASK, DOT = 1, 2, 4, 8, 16
+OVERLAP_WGRAD = True   # decoder weight-gradient GEMMs on a side stream, concurrent with the scatter kernels
+OVERLAP_PREP = True    # point sort + weight packing on the side stream, concurrent with the encoder
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(dev)
+    return _SIDE_STREAMS[key]
 USE_FUSED = True     # fused gather+decoder forward kernel when the decoder is 256/256/256
 USE_FUSED_BWD = True  # fused decoder backward-data chain (dz1, dz0, dfeat) when the decoder is 256/256/256
 SORT_MIN_POINTS = 2048   # spatially sort the query points of a scene when it has at least this many
@@ -695,6 +705,29 @@ def dense_eval(pyr, cache, x, vols, w0, b0, w1, b1, w2, b2, wo, bo, lattice, sce
     return out
 
 
+class QueryPrefetch:
+    """Work of the query path that does not depend on the encoder -- the spatial sort of the points and the bf16 / swizzled
+    copies of the decoder weights -- issued on a side stream so that it runs NEXT TO the encoder instead of after it."""
+
+    def __init__(self, pyr, cache: "PackedDecoder", points, w0, w1, w2):
+        pts = _dev_f32(points.detach(), "points")
+        dev = pts.device
+        self.pyr, self.pts_key = pyr, (pts.data_ptr(), tuple(pts.shape))
+        self._pts = pts                        # alive until the consumer has waited on `event`
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        ev = main.record_event()               # the points / weights are ready in main-stream order
+        with torch.cuda.device(dev), torch.cuda.stream(side), torch.autocast("cuda", enabled=False):
+            side.wait_event(ev)
+            self.perm = sort_points(pts) if pts.shape[1] >= SORT_MIN_POINTS else None
+            self.W = cache.get(pyr, w0, w1, w2)
+            self.event = side.record_event()
+        for t in ([self.perm] if self.perm is not None else []) + list(self.W.values()):
+            t.record_stream(main)
+
+    def matches(self, pyr, pts) -> bool:
+        return self.pyr is pyr and self.pts_key == (pts.data_ptr(), tuple(pts.shape))
+
+
 class _Query(torch.autograd.Function):
     """IFNet.forward given the encoder's volumes (ifnet.py:38-61,156-197): stencil gather + decoder.
 
@@ -703,14 +736,21 @@ class _Query(torch.autograd.Function):
 
     @staticmethod
     @_entry
-    def forward(ctx, pyr: PyramidSpec, cache: PackedDecoder, grad_mode: bool, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
+    def forward(ctx, pyr: PyramidSpec, cache: PackedDecoder, grad_mode, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols):
+        grad_mode, prefetched = grad_mode if isinstance(grad_mode, tuple) else (grad_mode, None)
         pts = _dev_f32(points, "points")
         x0 = _dev_f32(x, "x")
         B, N, _ = pts.shape
         M = B * N
         dev = pts.device
         packed = [pack_volume(v) for v in vols]
-        W = cache.get(pyr, w0, w1, w2)
+        if prefetched is not None and not prefetched.matches(pyr, pts):
+            prefetched = None
+        if prefetched is not None:
+            torch.cuda.current_stream(dev).wait_event(prefetched.event)
+            W = prefetched.W
+        else:
+            W = cache.get(pyr, w0, w1, w2)
         h0n, h1n, h2n = w0.shape[0], w1.shape[0], w2.shape[0]
         b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
         wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
@@ -719,7 +759,9 @@ class _Query(torch.autograd.Function):
         needs_bwd = bool(grad_mode) and any(ctx.needs_input_grad)
         perm = None
         if USE_FUSED and "w0p_img" in W:
-            if N >= SORT_MIN_POINTS:
+            if prefetched is not None:
+                perm = prefetched.perm
+            elif N >= SORT_MIN_POINTS:
                 perm = sort_points(pts)
             logits, hs, feat = fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save=needs_bwd, perm=perm,
                                              halo=halo_volumes(vols))
@@ -764,15 +806,36 @@ class _Query(torch.autograd.Function):
 
         def colsum(a, n):
             out = torch.empty((n,), device=dev, dtype=torch.float32)
-            _abi.check(_lib().svr_colsum_bf16(a.data_ptr(), M, n, a.stride(0), out.data_ptr(), 0, st), "colsum")
+            _abi.check(_lib().svr_colsum_bf16(a.data_ptr(), M, n, a.stride(0), out.data_ptr(), 0, _stream()), "colsum")
             return out
 
-        gw2 = torch.empty((h2n, h1n), device=dev, dtype=torch.float32)
-        _gemm_tn(dz2, h1, h2n, h1n, M, gw2)
-        gb2 = colsum(dz2, h2n)
+        def weight_grads(which):
+            """Weight / bias gradients of fc_2 (which = 2) or of fc_1 and fc_0 (which = 1) on the CURRENT stream."""
+            if which == 2:
+                g = torch.empty((h2n, h1n), device=dev, dtype=torch.float32)
+                _gemm_tn(dz2, h1, h2n, h1n, M, g)
+                return g, colsum(dz2, h2n)
+            g1 = torch.empty((h1n, h0n), device=dev, dtype=torch.float32)
+            _gemm_tn(dz1, h0, h1n, h0n, M, g1)
+            b1_ = colsum(dz1, h1n)
+            g0p = torch.empty((h0n, pyr.kp), device=dev, dtype=torch.float32)
+            _gemm_tn(dz0, feat, h0n, pyr.kp, M, g0p)
+            g0 = torch.empty((h0n, pyr.k), device=dev, dtype=torch.float32)
+            _abi.check(_lib().svr_unpack_w0_grad(g0p.data_ptr(), h0n, C.byref(pyr.c), g0.data_ptr(), _stream()), "unpack_w0_grad")
+            return g1, b1_, g0, colsum(dz0, h0n)
+
         need_dfeat = any(m[2] for m in ctx.vol_meta) or ctx.x_needs or ctx.p_needs
         dfeat = None
         fused_bwd = USE_FUSED_BWD and "w0pT_img" in W
+        # The weight-gradient GEMMs (tensor / HBM bound, small grids) are independent of the scatter (atomics / latency
+        # bound): with OVERLAP_WGRAD they run on a side stream next to it instead of in front of it.
+        overlap = OVERLAP_WGRAD and fused_bwd and need_dfeat
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if overlap else None
+        if overlap:
+            ev_head = main.record_event()
+        else:
+            gw2, gb2 = weight_grads(2)
         if fused_bwd:   # dz1, dz0 and dfeat in one persistent kernel
             dz1, dz0, dfeat = decoder_bwd_fused(dz2, h1, h0, W["w2T_img"], W["w1T_img"], W["w0pT_img"], pyr.kp)
         else:
@@ -780,14 +843,18 @@ class _Query(torch.autograd.Function):
             dz0 = torch.empty((M, h0n), device=dev, dtype=_BF16)
             _gemm_nt(dz2, W["w2T"], None, M, h1n, h2n, ST_BF16 | MASK, c_bf16=dz1, ldc=h1n, mask=h1)
             _gemm_nt(dz1, W["w1T"], None, M, h0n, h1n, ST_BF16 | MASK, c_bf16=dz0, ldc=h0n, mask=h0)
-        gw1 = torch.empty((h1n, h0n), device=dev, dtype=torch.float32)
-        _gemm_tn(dz1, h0, h1n, h0n, M, gw1)
-        gb1 = colsum(dz1, h1n)
-        gw0p = torch.empty((h0n, pyr.kp), device=dev, dtype=torch.float32)
-        _gemm_tn(dz0, feat, h0n, pyr.kp, M, gw0p)
-        gw0 = torch.empty((h0n, pyr.k), device=dev, dtype=torch.float32)
-        _abi.check(_lib().svr_unpack_w0_grad(gw0p.data_ptr(), h0n, C.byref(pyr.c), gw0.data_ptr(), st), "unpack_w0_grad")
-        gb0 = colsum(dz0, h0n)
+        if overlap:
+            ev_chain = main.record_event()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_head)
+                gw2, gb2 = weight_grads(2)
+                side.wait_event(ev_chain)
+                gw1, gb1, gw0, gb0 = weight_grads(1)
+                ev_side = side.record_event()
+            for t in (gw2, gb2, gw1, gb1, gw0, gb0):      # allocated on the side stream, consumed on the main stream
+                t.record_stream(main)
+        else:
+            gw1, gb1, gw0, gb0 = weight_grads(1)
         # d features, then scatter-add into the volumes
         any_vol = any(m[2] for m in ctx.vol_meta)
         gvols_out: List[Optional[torch.Tensor]] = [None] * len(packed)
@@ -820,6 +887,8 @@ class _Query(torch.autograd.Function):
                 _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
                                                  None, coarse_t, None, st), "gather_bwd")
             gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
+        if overlap:
+            main.wait_event(ev_side)
         return (None, None, None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
 
 
@@ -962,7 +1031,7 @@ class _Query32(torch.autograd.Function):
         return (None, gp, gx, gw0.view(s0), gb0, gw1.view(s1), gb1, gw2.view(s2), gb2, gwo.view(so), gbo, *gvols_out)
 
 
-def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols, precision=16):
+def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols, precision=16, prefetched=None):
     """``precision`` 16: bf16 operands on the tensor cores (logits within 1e-2 of the fp32 reference); 32: the fp32-accurate
     tier (1e-3)."""
     if points.shape[0] * points.shape[1] == 0:          # empty query set: nothing to launch (ifnet.py:38-61 returns (B, 0))
@@ -971,7 +1040,7 @@ def query(pyr, cache, points, x, w0, b0, w1, b1, w2, b2, wo, bo, vols, precision
         return points.new_zeros((points.shape[0], points.shape[1]), dtype=torch.float32)
     if int(precision) == 32:
         return _Query32.apply(pyr, points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
-    return _Query.apply(pyr, cache, torch.is_grad_enabled(), points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
+    return _Query.apply(pyr, cache, (torch.is_grad_enabled(), prefetched), points, x, w0, b0, w1, b1, w2, b2, wo, bo, *vols)
 
 
 class _Gather(torch.autograd.Function):

@@ -382,9 +382,24 @@ def test_first_stage_fused_conv_relu_bn(shape, zero_gamma):
         assert rel(y, yr) < 1e-4
         assert rel(bn.running_mean, bn_r.running_mean) < 1e-5 and rel(bn.running_var, bn_r.running_var) < 1e-5
         assert int(bn.num_batches_tracked) == int(bn_r.num_batches_tracked) == 1
-        for a, b in ((conv.weight.grad, conv_r.weight.grad), (conv.bias.grad, conv_r.bias.grad), (bn.weight.grad, bn_r.weight.grad),
-                     (bn.bias.grad, bn_r.bias.grad)):
-            assert rel(a, b) < 2e-4, rel(a, b)
+        # the gradients are judged against an fp64 evaluation of the same two modules (ground truth for both fp32
+        # implementations); the message also carries cuDNN's own fp32 deviation and how close any pre-activation is to
+        # the ReLU kink, so that a failure says which side moved
+        c64, b64 = copy.deepcopy(conv_r).double(), copy.deepcopy(bn_r).double()
+        b64.reset_running_stats()
+        for p in list(c64.parameters()) + list(b64.parameters()):
+            p.grad = None
+        pre64 = c64(x.double())
+        y64 = b64(torch.relu(pre64))
+        ((y64 * cot.double()).sum() + (torch.nn.functional.max_pool3d(y64, 2) * cot_p.double()).sum()).backward()
+        names = ("conv.weight", "conv.bias", "bn.weight", "bn.bias")
+        mine = (conv.weight.grad, conv.bias.grad, bn.weight.grad, bn.bias.grad)
+        cudnn = (conv_r.weight.grad, conv_r.bias.grad, bn_r.weight.grad, bn_r.bias.grad)
+        truth = (c64.weight.grad, c64.bias.grad, b64.weight.grad, b64.bias.grad)
+        for n, a, b, t in zip(names, mine, cudnn, truth):
+            ra, rb = rel(a.double(), t), rel(b.double(), t)
+            assert ra < 2e-4, (f"{n}: fused stage vs fp64 {ra:.3e}, torch fp32 vs fp64 {rb:.3e}, "
+                               f"min |pre-activation| {float(pre64.detach().abs().min()):.3e}, cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}")
         # eval mode: running statistics, forward only
         bn.eval(), bn_r.eval()
         with torch.no_grad():
