@@ -134,8 +134,11 @@ int svr_gather_fwd(const float *points, int B, int N, const float *x0, const uin
                    const svr_pyramid *pyr_host, uint16_t *feat, void *stream);
 /* Backward of the gather: dfeat (B*N, KP) bf16 -> scatter-add into gvols[l] (fp32 NDHWC, l>=1),
  * gx0 (fp32, may be NULL) and gpoints (B,N,3; may be NULL, needs x0/vols).  Outputs are
- * accumulated into (caller zero-fills).  perm (optional): row r of dfeat belongs to point perm[r]. */
-int svr_gather_bwd(const float *points, const int *perm, int B, int N, const float *x0,
+ * accumulated into (caller zero-fills).  perm (optional): row r of dfeat belongs to point perm[r];
+ * cell_start (optional, with perm): the row ranges of the sort cells written by svr_sort_points -- the
+ * tensor-core scatter of the coarse levels then cuts its row tiles at the boundaries of 2x2x2 cell
+ * groups, which bounds the voxel box a tile touches. */
+int svr_gather_bwd(const float *points, const int *perm, const int *cell_start, int B, int N, const float *x0,
                    const uint16_t *const *vols_host, const svr_pyramid *pyr_host, const uint16_t *dfeat,
                    float *gx0, float *const *gvols_host, float *gpoints, void *stream);
 
@@ -158,7 +161,11 @@ int svr_maxpool2_cl_bwd(const float *gout, const uint32_t *idx, int B, int D, in
  * Morton code of a 16^3 cell), so that consecutive rows are spatial neighbours (cache locality of
  * the gather; the reference has no counterpart -- every row is independent, results do not change).*/
 size_t svr_sort_points_workspace_bytes(int B, int N);
-int svr_sort_points(const float *points, int B, int N, int *perm, void *workspace, size_t workspace_bytes, void *stream);
+int svr_sort_cells_per_scene(void);
+/* cell_start (optional): B * svr_sort_cells_per_scene() + 1 ints, first sorted row of every (scene, cell)
+ * in sort order, then B*N. */
+int svr_sort_points(const float *points, int B, int N, int *perm, int *cell_start, void *workspace, size_t workspace_bytes,
+                    void *stream);
 
 /* tcgen05 GEMMs (Conv1d k=1 of ifnet.py:55-59 and their backward).
  * NT:  C[M,N] = epi( A[M,K] . B[N,K]^T + bias[N] ),  A,B bf16 row-major, K % 64 == 0.

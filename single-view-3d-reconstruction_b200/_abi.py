@@ -57,14 +57,15 @@ _SIGS = {
     "svr_unpack_w0_grad": (C.c_int, [vp, C.c_int, C.POINTER(Pyramid), vp, vp]),
     "svr_pack_matrix": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
     "svr_gather_fwd": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), vp, vp]),
-    "svr_gather_bwd": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), vp, vp, C.POINTER(vp), vp, vp]),
+    "svr_gather_bwd": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(Pyramid), vp, vp, C.POINTER(vp), vp, vp]),
     "svr_conv1_relu_fwd": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "svr_conv1_relu_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
     "svr_conv1_relu_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t, vp]),
     "svr_maxpool2_cl_fwd": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "svr_maxpool2_cl_bwd": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "svr_sort_points_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
-    "svr_sort_points": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
+    "svr_sort_cells_per_scene": (C.c_int, []),
+    "svr_sort_points": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]),
     "svr_gemm_nt": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int64, vp,
                               vp, vp, vp, vp]),
     "svr_gemm_tn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -106,7 +107,8 @@ _lib = None
 KERNELS_PER_CALL = {
     "svr_unproject_fwd": 1, "svr_unproject_bwd": 1, "svr_norm_grid_space": 1, "svr_voxelize_fwd": 9, "svr_voxelize_bwd": 1,
     "svr_blur_fwd": 3, "svr_blur_bwd": 12, "svr_pack_volume": 1, "svr_pack_volume_halo": 1, "svr_unpack_volume_grad": 1, "svr_pack_w0": 1,
-    "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 1, "svr_gemm_nt": 1, "svr_gemm_tn": 2,
+    "svr_unpack_w0_grad": 1, "svr_pack_matrix": 1, "svr_gather_fwd": 1, "svr_gather_bwd": 1, "svr_gather_bwd[tensor-core]": 2,
+    "svr_gemm_nt": 1, "svr_gemm_tn": 2,
     "svr_decoder_head_bwd": 2, "svr_colsum_bf16": 2, "svr_query_fwd_fused": 1, "svr_dense_eval": 1, "svr_decoder_bwd_fused": 1, "svr_pack_decoder_image": 1, "svr_sort_points": 4, "svr_bias_relu_cl": 1, "svr_widen_bf16": 1, "svr_relu_bwd_cl": 2, "svr_conv1_relu_fwd": 1, "svr_conv1_relu_bwd": 2, "svr_conv1_relu_bn_stats": 2, "svr_conv1_relu_bn_apply": 1, "svr_conv1_relu_bn_bwd": 4, "svr_maxpool2_cl_fwd": 1, "svr_maxpool2_cl_bwd": 1,
     "svr_split_bf16": 1, "svr_pack_w0_f32": 1, "svr_gather_fwd_f32": 1, "svr_gather_bwd_f32": 1, "svr_decoder_head_bwd_f32": 3, "svr_colsum_f32": 2,
 }
@@ -157,7 +159,7 @@ class _Lib:
         def call(*a):
             prof = PROFILE
             key, prof.label = (prof.label or name), None
-            prof.launches[key] = prof.launches.get(key, 0) + n_k
+            prof.launches[key] = prof.launches.get(key, 0) + KERNELS_PER_CALL.get(key, n_k)
             prof.calls[key] = prof.calls.get(key, 0) + 1
             if prof.events is None:
                 return fn(*a)

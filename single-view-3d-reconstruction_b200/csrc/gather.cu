@@ -6,8 +6,8 @@
 
 namespace svr {
 
-int launch_scatter_tc(const float *points, const int *perm, int N, int64_t total_rows, const Pyr &P, const __nv_bfloat16 *dfeat,
-                      float *const *gvols, int level_mask, cudaStream_t st);   // scatter_tc.cu
+int launch_scatter_tc(const float *points, const int *perm, const int *cell_start, int n_cells, int N, int64_t total_rows, const Pyr &P,
+                      const __nv_bfloat16 *dfeat, float *const *gvols, int level_mask, cudaStream_t st);   // scatter_tc.cu
 
 struct VolPtrs {
     const __nv_bfloat16 *v[SVR_MAX_LEVELS];
@@ -413,7 +413,7 @@ int svr_gather_fwd(const float *points, int B, int N, const float *x0, const uin
     return 0;
 }
 
-int svr_gather_bwd(const float *points, const int *perm, int B, int N, const float *x0, const uint16_t *const *vols_host,
+int svr_gather_bwd(const float *points, const int *perm, const int *cell_start, int B, int N, const float *x0, const uint16_t *const *vols_host,
                    const svr_pyramid *pyr_host, const uint16_t *dfeat, float *gx0, float *const *gvols_host, float *gpoints,
                    void *stream) {
     Pyr P;
@@ -434,7 +434,8 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
     int agg_mask = 0;
     if (perm && gvols_host)
         for (int l = 1; l < P.n_levels; ++l)
-            if (gp.g[l] && (int64_t)P.D[l] * P.H[l] * P.W[l] <= 40 * 40 * 40) agg_mask |= 1 << l;
+            if (gp.g[l] && (int64_t)P.D[l] * P.H[l] * P.W[l] <= 40 * 40 * 40 && P.C[l] >= 16 && P.C[l] <= 128 && (P.C[l] & (P.C[l] - 1)) == 0)
+                agg_mask |= 1 << l;
     const int direct_mask = ~agg_mask;
     bool direct_needed = gpoints || gx0;
     for (int l = 1; l < P.n_levels; ++l)
@@ -468,7 +469,9 @@ int svr_gather_bwd(const float *points, const int *perm, int B, int N, const flo
                                                                             u_lo, u_cnt);
     }
     if (agg_mask)
-        if (int rc = launch_scatter_tc(points, perm, N, total_pts, P, (const __nv_bfloat16 *)dfeat, gp.g, agg_mask, as_stream(stream))) return rc;
+        if (int rc = launch_scatter_tc(points, perm, cell_start, B * svr_sort_cells_per_scene(), N, total_pts, P, (const __nv_bfloat16 *)dfeat,
+                                       gp.g, agg_mask, as_stream(stream)))
+            return rc;
     SVR_LAUNCH_CHECK();
     return 0;
 }

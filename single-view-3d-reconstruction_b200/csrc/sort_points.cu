@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) sort_count_kernel(const float *__r
 }
 
 // exclusive scan of `n` ints by ONE block of 1024 threads (n = B * 4096, a few thousand entries)
-__global__ void __launch_bounds__(1024) sort_scan_kernel(const int *__restrict__ in, int *__restrict__ out, int n) {
+__global__ void __launch_bounds__(1024) sort_scan_kernel(const int *__restrict__ in, int *__restrict__ out, int n, int *__restrict__ total_out) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s, chunk_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(const int *__restrict__
         if (threadIdx.x == 0) carry_s += chunk_s;
         __syncthreads();
     }
+    if (total_out && threadIdx.x == 0) *total_out = carry_s;
 }
 
 // one thread per (scene, key): exclusive prefix of the key's per-block counts, in place
@@ -141,14 +142,19 @@ size_t svr_sort_points_workspace_bytes(int B, int N) {
     return ((((size_t)B * N + 63) / 64) * 64 + 2 * nkeys + nkeys * (size_t)sort_nblk(N)) * sizeof(int) + 1024;
 }
 
-int svr_sort_points(const float *points, int B, int N, int *perm, void *workspace, size_t workspace_bytes, void *stream) {
+int svr_sort_cells_per_scene(void) { return SORT_KEYS; }
+
+int svr_sort_points(const float *points, int B, int N, int *perm, int *cell_start, void *workspace, size_t workspace_bytes, void *stream) {
     SVR_REQUIRE(points && perm && workspace, "sort_points: null pointer");
     SVR_REQUIRE((int64_t)B * N < ((int64_t)1 << 31), "sort_points: too many points");
     SVR_REQUIRE(workspace_bytes >= svr_sort_points_workspace_bytes(B, N), "sort_points: workspace too small");
     const int64_t total = (int64_t)B * N;
-    if (total == 0) return 0;
     cudaStream_t st = as_stream(stream);
     const int nkeys = B * SORT_KEYS, nblk = sort_nblk(N);
+    if (total == 0) {
+        if (cell_start && B > 0) SVR_CUDA(cudaMemsetAsync(cell_start, 0, ((size_t)nkeys + 1) * sizeof(int), st));
+        return 0;
+    }
     SVR_REQUIRE((int64_t)B * nblk < ((int64_t)1 << 31), "sort_points: too many blocks");
     int *key_rank = (int *)workspace;
     int *count = key_rank + (((size_t)total + 63) / 64) * 64;
@@ -156,9 +162,12 @@ int svr_sort_points(const float *points, int B, int N, int *perm, void *workspac
     int *hist = start + nkeys;
     SVR_CUDA(cudaMemsetAsync(count, 0, (size_t)nkeys * sizeof(int), st));
     sort_count_kernel<<<(unsigned)(B * nblk), SORT_BLOCK, 0, st>>>(points, N, nblk, key_rank, count, hist);
-    sort_scan_kernel<<<1, 1024, 0, st>>>(count, start, nkeys);
+    sort_scan_kernel<<<1, 1024, 0, st>>>(count, start, nkeys, cell_start ? cell_start + nkeys : nullptr);
     sort_block_prefix_kernel<<<(unsigned)ceil_div(nkeys, 256), 256, 0, st>>>(hist, nkeys, nblk);
     sort_fill_kernel<<<(unsigned)(B * nblk), SORT_BLOCK, 0, st>>>(key_rank, N, nblk, start, hist, perm);
+    if (cell_start) {      // first sorted row of every (scene, cell) + the total: the row ranges of spatial groups
+        SVR_CUDA(cudaMemcpyAsync(cell_start, start, (size_t)nkeys * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
     SVR_LAUNCH_CHECK();
     return 0;
 }

@@ -631,11 +631,26 @@ SORT_MIN_POINTS = 2048   # spatially sort the query points of a scene when it ha
 def sort_points(pts: torch.Tensor) -> torch.Tensor:
     """(B,N,3) -> int32 (B*N,) processing order (scene-major, Morton order of 16^3 cells inside a scene)."""
     B, N, _ = pts.shape
-    perm = torch.empty((B * N,), device=pts.device, dtype=torch.int32)
+    # one buffer: the order, then the first sorted row of every (scene, cell) + the total (read by the scatter, which
+    # cuts its row tiles at cell-group boundaries; see sort_cells_ptr)
+    buf = torch.empty((B * N + B * _lib().svr_sort_cells_per_scene() + 1,), device=pts.device, dtype=torch.int32)
+    perm = buf[:B * N]
     nbytes = _lib().svr_sort_points_workspace_bytes(B, N)
     ws = torch.empty((nbytes,), device=pts.device, dtype=torch.uint8)
-    _abi.check(_lib().svr_sort_points(pts.data_ptr(), B, N, perm.data_ptr(), ws.data_ptr(), nbytes, _stream()), "sort_points")
+    _abi.check(_lib().svr_sort_points(pts.data_ptr(), B, N, perm.data_ptr(), perm.data_ptr() + 4 * B * N, ws.data_ptr(), nbytes, _stream()),
+               "sort_points")
     return perm
+
+
+def sort_cells_ptr(perm, B: int):
+    """Address of the cell table that ``sort_points`` stores behind the order (None for an order from elsewhere)."""
+    if perm is None:
+        return None
+    M, cells = perm.numel(), B * _lib().svr_sort_cells_per_scene() + 1
+    st = perm.untyped_storage()
+    if perm.storage_offset() != 0 or st.nbytes() < 4 * (M + cells):
+        return None
+    return perm.data_ptr() + 4 * M
 
 
 def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, sigmoid: bool = False, perm=None, halo=None):
@@ -879,13 +894,13 @@ class _Query(torch.autograd.Function):
             fine_t = _abi.ptr_table([None] + [None if c else _ptr(g) for g, c in zip(gbufs, coarse)])
             if gx is not None or gp is not None or any(g is not None and not c for g, c in zip(gbufs, coarse)):
                 _abi.PROFILE.label = "svr_gather_bwd[direct]"
-                _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
+                _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), None, B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
                                                  _ptr(gx), fine_t, _ptr(gp), st), "gather_bwd")
             if any(coarse):
                 coarse_t = _abi.ptr_table([None] + [_ptr(g) if c else None for g, c in zip(gbufs, coarse)])
                 _abi.PROFILE.label = "svr_gather_bwd[tensor-core]"
-                _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(),
-                                                 None, coarse_t, None, st), "gather_bwd")
+                _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), _ptr(perm), sort_cells_ptr(perm, B), B, N, x0.data_ptr(), vt, C.byref(pyr.c),
+                                                 dfeat.data_ptr(), None, coarse_t, None, st), "gather_bwd")
             gvols_out = [g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs]
         if overlap:
             main.wait_event(ev_side)
@@ -1074,7 +1089,7 @@ class _Gather(torch.autograd.Function):
         gp = torch.zeros_like(pts) if ctx.p_needs else None
         vt = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
         gt = _abi.ptr_table([None] + [_ptr(g) for g in gbufs])
-        _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), None, B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
+        _abi.check(_lib().svr_gather_bwd(pts.data_ptr(), None, None, B, N, x0.data_ptr(), vt, C.byref(pyr.c), dfeat.data_ptr(), _ptr(gx), gt,
                                          _ptr(gp), _stream()), "gather_bwd")
         return (None, gp, gx, *[g.permute(0, 4, 1, 2, 3) if g is not None else None for g in gbufs])
 

@@ -208,6 +208,40 @@ def test_bench_path_128cube_vs_oracle(precision, train):
     assert not bad, bad
 
 
+def test_scatter_row_tiles_on_clustered_and_out_of_range_points():
+    """The tensor-core scatter cuts its row tiles at the boundaries of 2x2x2 groups of sort cells.  Point sets that make
+    the groups very uneven: scene 0 has every point inside a 0.1-wide cube (a handful of groups with thousands of rows
+    each -> many tiles per group, all other groups empty); scene 1 mixes points beyond the volume (|p| up to 0.6), points
+    on one plane and exact duplicates.  Logits and the scattered tensors (volume gradients of every level, dx, dpts) vs
+    the fp32 oracle; the decoder's weight gradients are checked on well-spread points by the tests above (on thousands of
+    near-identical rows one ReLU decision that differs in bf16 is multiplied by the cluster size)."""
+    sd = R.synthetic_state_dict(47, 128)
+    net = _net(128, sd).eval()
+    g = torch.Generator().manual_seed(23)
+    x = ((torch.rand((2, 1, 128, 128, 128), generator=g) < 0.05).float()).cuda()
+    n = 6000
+    p0 = torch.tensor([0.2, -0.3, 0.1]) + (torch.rand((n, 3), generator=g) - 0.5) * 0.1
+    far = (torch.rand((n // 3, 3), generator=g) - 0.5) * 1.2
+    plane = (torch.rand((n // 3, 3), generator=g) - 0.5)
+    plane[:, 1] = 0.25
+    rest = n - 2 * (n // 3)
+    dup = torch.cat([far[:1].repeat(64, 1) * 0.5, (torch.rand((rest - 64, 3), generator=g) - 0.5)])
+    pts = torch.stack([p0, torch.cat([far, plane, dup])]).cuda()
+    cot = torch.randn((2, n), generator=g).cuda()
+    with torch.no_grad():
+        vols = net.encode(x)
+    ref, rg, _ = _oracle_hot_path(sd, x, vols, pts, cot)
+    got, gg = _device_hot_path(net, x, vols, pts, cot)
+    assert _rel(got, ref) < TOL_BF16
+    bad = {}
+    for name, r in rg.items():
+        e = _rel_l2(gg[name].reshape(r.shape), r)
+        _record(f"clustered/{name}", e)
+        if name[0] == "d" and not e < BF16_GRAD_TOL:
+            bad[name] = e
+    assert not bad, bad
+
+
 def test_config2_size_scene_additivity_and_reproducibility():
     """BASELINE config 2 at full size (4 scenes x 50 000 points, 128^3), forward + backward through the sorted /
     tensor-core-scatter path.  Size-independent properties: (a) scenes are independent, so the batch's weight
