@@ -215,11 +215,21 @@ int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *im
 int svr_debug_fq_trace(void *buf);
 
 /* halo_vols_host (nullable table, nullable entries): svr_pack_volume_halo copies of the levels with
- * C % 64 == 0; the trailing run of such levels is sampled through the kernel's bounds-check-free wide path  */
-int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, const float *x0,
+ * C % 64 == 0; the trailing run of such levels is sampled through the kernel's bounds-check-free wide path.
+ * cell_start (optional, with perm): the row ranges of the sort cells written by svr_sort_points; used by the box
+ * kernel (svr_debug_fq_interp(2)), which cuts row tiles at the boundaries of sort-cell groups.                      */
+int svr_query_fwd_fused(const float *points, const int *perm, const int *cell_start, int B, int N, const float *x0,
                         const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host,
                         const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, float *logits,
                         uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream);
+/* Kernel choice.  0: every level gathered on the CUDA cores.  1 (default): svr_dense_eval runs the box kernel -- the
+ * levels whose voxel box per 128-point brick is small (32^3 / 16^3 / 8^3 of the 128-net) are interpolated on the tensor
+ * cores from a box staged in shared memory (bf16 trilinear weights) instead of gathered corner by corner.  2: explicit
+ * points with a sort-cell table take the box kernel too (slower than the gather kernel at 50k points per scene: the
+ * tiles cut at cell-group boundaries are 77 % full).                                                        */
+int svr_debug_fq_interp(int mode);
+/* debug: the block whose timeline svr_debug_fq_trace records (default 0) */
+int svr_debug_fq_trace_block(int block);
 
 /* First stage of the 128-net fused: y = BatchNorm3d(relu(Conv3d(1 -> 16, 3, padding 1)(x))), channels-last y
  * (model/ifnet.py:126,137,164 `net = self.actvn(self.conv_in(x)); net = self.conv_in_bn(net)`).  The pre-BN

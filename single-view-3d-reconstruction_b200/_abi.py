@@ -74,7 +74,7 @@ _SIGS = {
     "svr_decoder_head_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "svr_colsum_bf16": (C.c_int, [vp, C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp]),
     "svr_pack_decoder_image": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
-    "svr_query_fwd_fused": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Pyramid),
+    "svr_query_fwd_fused": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Pyramid),
                                       C.POINTER(DecoderWeights), vp, vp, vp, C.c_int, vp]),
     "svr_conv1_bn_workspace_bytes": (C.c_size_t, []),
     "svr_conv1_relu_bn_stats": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp,
@@ -89,6 +89,8 @@ _SIGS = {
     "svr_decoder_bwd_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp]),
     "svr_debug_fb_trace": (C.c_int, [vp]),
     "svr_debug_fq_trace": (C.c_int, [vp]),
+    "svr_debug_fq_interp": (C.c_int, [C.c_int]),
+    "svr_debug_fq_trace_block": (C.c_int, [C.c_int]),
     "svr_dense_eval": (C.c_int, [C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Pyramid), C.POINTER(DecoderWeights),
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     # fp32-accurate tier (csrc/precise.cu)

@@ -614,6 +614,21 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
 }
 
 static long long *g_fq_trace = nullptr;
+// 0: every level gathered on the CUDA cores (this file's kernel).  1 (default): the dense evaluator runs the box kernel
+// (fused_query_box.cu: coarse levels interpolated on the tensor cores from voxel boxes staged in shared memory).
+// 2: explicit query points take the box kernel too when they come with the sort-cell table.
+static int g_fq_interp = 1;
+
+namespace fqb {
+void set_interp(int on);
+void set_trace(long long *buf, int block);
+int query_fwd(const float *points, const int *perm, const int *cell_start, int B, int N, const float *x0,
+              const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host, const svr_pyramid *pyr_host,
+              const svr_decoder_weights *w_host, float *logits, uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream);
+int dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host,
+               const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, int sx, int sy, int sz, int x_begin, int x_end, float *out,
+               void *stream);
+}  // namespace fqb
 
 static int fq_launch(const FqParams &p, int64_t n_tiles, cudaStream_t st) {
     static DeviceOnce once;
@@ -641,6 +656,18 @@ extern "C" {
 /* debug: per-role (tag, SM clock) records of block 0 of the next fused query launches; buf = 4 x 1024 x 2 int64 (device), null = off */
 int svr_debug_fq_trace(void *buf) {
     g_fq_trace = (long long *)buf;
+    fqb::set_trace((long long *)buf, 0);
+    return 0;
+}
+
+int svr_debug_fq_trace_block(int block) {
+    fqb::set_trace(g_fq_trace, block);
+    return 0;
+}
+
+int svr_debug_fq_interp(int mode) {
+    g_fq_interp = mode;
+    fqb::set_interp(mode != 0);
     return 0;
 }
 
@@ -653,9 +680,14 @@ int svr_pack_decoder_image(const uint16_t *w_rowmajor, int R, int K, uint8_t *im
     return 0;
 }
 
-int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, const float *x0, const uint16_t *const *vols_host,
-                        const uint16_t *const *halo_vols_host, const svr_pyramid *pyr_host, const svr_decoder_weights *w_host,
-                        float *logits, uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid, void *stream) {
+int svr_query_fwd_fused(const float *points, const int *perm, const int *cell_start, int B, int N, const float *x0,
+                        const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host, const svr_pyramid *pyr_host,
+                        const svr_decoder_weights *w_host, float *logits, uint16_t *save_h, uint16_t *save_feat, int apply_sigmoid,
+                        void *stream) {
+    SVR_REQUIRE(!cell_start || perm, "query_fwd_fused: cell_start needs the order it belongs to");
+    if (g_fq_interp == 2 && cell_start)
+        return fqb::query_fwd(points, perm, cell_start, B, N, x0, vols_host, halo_vols_host, pyr_host, w_host, logits, save_h, save_feat,
+                              apply_sigmoid, stream);
     FqParams p{};
     if (int rc = fq_fill(p, x0, vols_host, halo_vols_host, pyr_host, w_host)) return rc;
     SVR_REQUIRE(points && logits, "query_fwd_fused: null pointer");
@@ -673,6 +705,7 @@ int svr_query_fwd_fused(const float *points, const int *perm, int B, int N, cons
 int svr_dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host,
                    const svr_pyramid *pyr_host, const svr_decoder_weights *w_host, int sx, int sy, int sz, int x_begin, int x_end,
                    float *out, void *stream) {
+    if (g_fq_interp) return fqb::dense_eval(scene, B, x0, vols_host, halo_vols_host, pyr_host, w_host, sx, sy, sz, x_begin, x_end, out, stream);
     FqParams p{};
     if (int rc = fq_fill(p, x0, vols_host, halo_vols_host, pyr_host, w_host)) return rc;
     SVR_REQUIRE(out && scene >= 0 && scene < B, "dense_eval: bad scene index");

@@ -14,25 +14,21 @@
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tc05.cuh"
+#include "tiles.cuh"
 
 #include <type_traits>
 
 namespace svr {
 using namespace tc;
 
-constexpr int ST_TILE = 128, ST_THREADS = 256, ST_TMEM_COLS = 256;
+constexpr int ST_THREADS = 256, ST_TMEM_COLS = 256;
 constexpr int ST_A_BYTES = 128 * 128 * 2;   // S_d^T tile: 128 voxels x 128 rows bf16 (two 64-row K chunks, filled and consumed alternately)
 constexpr int ST_B_BYTES = 128 * 128 * 2;   // dF slice: 128 rows x up to 128 channels bf16 (double buffered)
 constexpr int ST_MAX_VOX = 1024;            // larger boxes fall back to direct reductions
 constexpr int ST_SMEM = 1024 + ST_A_BYTES + 2 * ST_B_BYTES + ST_TILE * 16 + 256;
-constexpr int ST_SUPER = 8;                 // sort cells per tile group: 2x2x2 Morton-adjacent cells of the 16^3 sort grid
 
 struct StGrad {
     float *g[SVR_MAX_LEVELS];
-};
-
-struct StTile {
-    int row0, rows;
 };
 
 __device__ __forceinline__ void st_red_add_v4(float *addr, float a, float b, float c, float d) {
@@ -347,6 +343,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2) scatter_tc_kernel(const float *
     }
 }
 
+int launch_st_tiles(const int *cell_start, int n_groups, StTile *tiles, int *n_tiles, cudaStream_t st) {
+    st_tiles_kernel<<<1, 1024, 0, st>>>(cell_start, n_groups, tiles, n_tiles);
+    SVR_LAUNCH_CHECK();
+    return 0;
+}
+
 // cell_start: first sorted row of every (scene, sort cell), n_cells + 1 entries (svr_sort_points), or nullptr: fixed
 // tiles of 128 consecutive rows
 int launch_scatter_tc(const float *points, const int *perm, const int *cell_start, int n_cells, int N, int64_t total_rows, const Pyr &P,
@@ -370,7 +372,7 @@ int launch_scatter_tc(const float *points, const int *perm, const int *cell_star
         if (int rc = scratch_alloc(&scratch, (size_t)n_tiles * sizeof(StTile) + 16, st)) return rc;
         count = (int *)scratch;
         tiles = (StTile *)((uint8_t *)scratch + 16);
-        st_tiles_kernel<<<1, 1024, 0, st>>>(cell_start, n_groups, tiles, count);
+        if (int rc = launch_st_tiles(cell_start, n_groups, tiles, count, st)) return rc;
     }
     scatter_tc_kernel<<<(unsigned)n_tiles, ST_THREADS, ST_SMEM, st>>>(points, perm, N, total_rows, P, dfeat, g, level_mask, tiles, count);
     SVR_LAUNCH_CHECK();

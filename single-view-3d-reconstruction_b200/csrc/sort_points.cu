@@ -9,6 +9,7 @@ namespace svr {
 
 constexpr int SORT_CELLS = 16;                                  // per axis
 constexpr int SORT_KEYS = SORT_CELLS * SORT_CELLS * SORT_CELLS;   // per scene
+constexpr float SORT_SHIFT = 0.125f;
 
 __device__ __forceinline__ uint32_t spread3(uint32_t v) {   // up to 5 bits -> every third bit
     v &= 0x1F;
@@ -22,7 +23,11 @@ __device__ __forceinline__ int point_key(const float *p) {
     uint32_t c[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float t = (p[k] + 0.5f) * (float)SORT_CELLS;
+        // The cell lattice is shifted by SORT_SHIFT cells against the voxel lattices of the coarse feature levels: a group
+        // of 2x2x2 cells plus the 7-point stencil then touches 5 (not 6) voxels per axis of a 16^3 level and 3 of an 8^3
+        // level (align_corners=False puts voxel centres at half-integer multiples of the cell size), 8 of a 32^3 level --
+        // the voxel boxes of the tensor-core interpolation / scatter (fused_query.cu, scatter_tc.cu) shrink 216 -> 125.
+        float t = (p[k] + 0.5f) * (float)SORT_CELLS - SORT_SHIFT;
         t = fminf(fmaxf(t, 0.f), (float)(SORT_CELLS - 1));   // NaN -> 0
         c[k] = (uint32_t)t;
     }

@@ -668,7 +668,7 @@ def fused_forward(pyr, W, pts, x0, packed, b0f, b1f, b2f, wof, bof, save: bool, 
     feat = torch.empty((M, pyr.kp), device=dev, dtype=_BF16) if save else None
     tbl = _abi.ptr_table([None] + [v.data_ptr() for v in packed])
     htbl = _abi.ptr_table([None] + [_ptr(v) for v in (halo or [])])
-    _abi.check(_lib().svr_query_fwd_fused(pts.data_ptr(), _ptr(perm), B, N, x0.data_ptr(), tbl, htbl, C.byref(pyr.c), C.byref(dw),
+    _abi.check(_lib().svr_query_fwd_fused(pts.data_ptr(), _ptr(perm), sort_cells_ptr(perm, B), B, N, x0.data_ptr(), tbl, htbl, C.byref(pyr.c), C.byref(dw),
                                           logits.data_ptr(), _ptr(h), _ptr(feat), int(sigmoid), _stream()), "query_fwd_fused")
     return logits, h, feat
 

@@ -280,24 +280,69 @@ def test_sorted_aggregated_backward_matches_direct():
     assert _rel_l2(b[4], a[4]) < 1e-4 and _rel_l2(b[5], a[5]) < 1e-4
 
 
-def test_fused_dense_evaluator_matches_chunked_query():
+@pytest.mark.parametrize("kernel", ["gather", "box"])
+def test_fused_dense_evaluator_matches_chunked_query(kernel):
     """svr_dense_eval (lattice generated in-kernel, brick order) against the chunked point path on the
-    same make_3d_grid points, incl. non-multiple-of-brick sizes, several scenes and an x-slab."""
+    same make_3d_grid points, incl. non-multiple-of-brick sizes, several scenes and an x-slab.  The gather kernel
+    (svr_debug_fq_interp(0)) runs the arithmetic of the point path: 1e-5.  The box kernel (default) interpolates the
+    coarse levels on the tensor cores with bf16 trilinear weights: 2e-4 on the occupancy probabilities here (the 1e-2
+    bound on the logits against the reference is tests/test_gpu_parity_r2.py::test_dense_eval_256cube_slab_vs_c_oracle)."""
     import svr_b200
+    from svr_b200 import _abi
     sd = R.synthetic_state_dict(31, 128)
     net = _net(128, sd).eval()
     g = torch.Generator().manual_seed(12)
     x = (torch.rand((2, 1, 32, 24, 16), generator=g) < 0.15).float().cuda()
-    for lattice in ((19, 10, 7), (32, 24, 16)):
-        dense = net.evaluate_grid(x, lattice)
-        assert dense.shape == (2, *lattice)
-        pts = svr_b200.make_3d_grid((-0.5,) * 3, (0.5,) * 3, lattice, 1).cuda()
-        with torch.no_grad():
-            vols = net.ifnet_feature_extractor.encode(x)
-            ref = torch.sigmoid(net.query(x, vols, pts[None].expand(2, -1, -1).contiguous())).view(2, *lattice)
-        assert float((dense - ref).abs().max()) < 1e-5
-        slab = net.evaluate_grid(x, lattice, scenes=[1], x_range=(8, 16))
-        assert torch.equal(slab[0, 8:16], dense[1, 8:16]) and float(slab[0, :8].abs().max()) == 0.0
+    _abi.load().svr_debug_fq_interp(0 if kernel == "gather" else 1)
+    try:
+        for lattice in ((19, 10, 7), (32, 24, 16)):
+            dense = net.evaluate_grid(x, lattice)
+            assert dense.shape == (2, *lattice)
+            pts = svr_b200.make_3d_grid((-0.5,) * 3, (0.5,) * 3, lattice, 1).cuda()
+            with torch.no_grad():
+                vols = net.ifnet_feature_extractor.encode(x)
+                ref = torch.sigmoid(net.query(x, vols, pts[None].expand(2, -1, -1).contiguous())).view(2, *lattice)
+            assert float((dense - ref).abs().max()) < (1e-5 if kernel == "gather" else 2e-4)
+            slab = net.evaluate_grid(x, lattice, scenes=[1], x_range=(8, 16))
+            assert torch.equal(slab[0, 8:16], dense[1, 8:16]) and float(slab[0, :8].abs().max()) == 0.0
+    finally:
+        _abi.load().svr_debug_fq_interp(1)
+
+
+def test_box_kernel_on_sorted_points_matches_gather_kernel():
+    """The box kernel on explicit (sorted) query points -- svr_debug_fq_interp(2): row tiles cut at sort-cell group
+    boundaries, 16^3 / 8^3 levels interpolated on the tensor cores -- against the gather kernel on a 128^3 scene pair
+    with out-of-range points and ragged tiles: logits to 3e-3 of the range, saved features to 5e-3 relative L2 (bf16
+    trilinear weights), and a backward pass through the features it saved."""
+    import svr_b200
+    from svr_b200 import _abi
+    sd = R.synthetic_state_dict(33, 128)
+    net = _net(128, sd).eval()
+    g = torch.Generator().manual_seed(13)
+    x = (torch.rand((2, 1, 128, 128, 128), generator=g) < 0.05).float().cuda()
+    pts = ((torch.rand((2, 6000, 3), generator=g) - 0.5) * 1.06).cuda()
+    pts[1, :1500] = pts[1, 0]                     # 1500 rows in one sort cell: several tiles with the same voxel box
+    res = {}
+    try:
+        for mode in (0, 2):
+            _abi.load().svr_debug_fq_interp(mode)
+            with torch.no_grad():
+                vols = net.ifnet_feature_extractor.encode(x)
+                out_i = net.query(x, vols, pts)
+            vv = [v.clone().requires_grad_(True) for v in vols]
+            out = net.query(x, vv, pts)
+            feat = out.grad_fn.saved_tensors[2].float()
+            out.backward(torch.ones_like(out))
+            res[mode] = (out_i, out.detach(), feat, [v.grad for v in vv])
+    finally:
+        _abi.load().svr_debug_fq_interp(1)
+    a, b = res[0], res[2]
+    scale = float(a[0].abs().max())
+    assert torch.equal(b[0], b[1])                # inference and training launches agree
+    assert float((a[0] - b[0]).abs().max()) / scale < 3e-3
+    assert _rel_l2(b[2], a[2]) < 5e-3
+    for ga, gb in zip(a[3], b[3]):
+        assert _rel_l2(gb, ga) < 2e-2
 
 
 def test_channels_last_maxpool_matches_torch():

@@ -23,13 +23,7 @@ with torch.no_grad():
 print("quarter scene ms", e0.elapsed_time(e1))
 b = buf.cpu()
 t0 = int(b[b[:, :, 1] > 0][:, 1].min())
-g = [(int(t), int(c) - t0) for t, c in b[0] if c > 0]
-arr = [(t - 200, c) for t, c in g if 200 <= t < 300][:90]
-prev = None
-out = []
-for t, c in arr:
-    out.append(f"{t}:{c}" + (f"(+{c - prev})" if prev is not None else ""))
-    prev = c
-print(" ".join(out))
-e = [(int(t), int(c) - t0) for t, c in b[2] if c > 0]
-print("epilogue", " ".join(f"{t}:{c}" for t, c in e[:12]))
+for role, name in enumerate(("producer warp 0", "mma", "epilogue warp 0", "prep warp")):
+    recs = [(int(t), int(c) - t0) for t, c in b[role] if c > 0]
+    print(name, len(recs))
+    print("  " + " ".join(f"{t}:{c}" for t, c in recs[:150]))
