@@ -280,10 +280,10 @@ def config_block(config: int, world: int):
 # ------------------------------------------------------------------------------------------------
 # rooflines (SURVEY.md 8(d) figures)
 # ------------------------------------------------------------------------------------------------
-def _ncu_traffic(kernel_substr: str):
+def _ncu_traffic(kernel_substr: str, files=("r2b_query_path.txt", "r2_query_path.txt", "r2_projection.txt", "r1_query_path_v4.txt")):
     """dram read + write bytes per launch of a kernel from the newest committed `ncu --set full` summary (profiles/)."""
     unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "Tbyte": 1e12}
-    for fname in ("r2_query_path.txt", "r2_projection.txt", "r1_query_path_v4.txt"):
+    for fname in files:
         f = ROOT / "profiles" / fname
         if not f.exists():
             continue
@@ -340,7 +340,17 @@ def query_rooflines(kms, peaks, M, n_scenes, training=True):
     add("svr_query_fwd_fused", "tensor", fwd_flops, peaks, "fused_query_kernel" if training else None,
         f"fused gather + fc_0..fc_out; compulsory HBM bytes {vols_bf16 + x_bytes + 16 * M} (bf16 volumes + grid + 16 B/point)"
         + ("; traffic = the training launch, which also streams the saved features / activations" if training else ""))
-    add("svr_dense_eval", "tensor", fwd_flops, peaks, None, "same kernel as svr_query_fwd_fused in lattice mode (nothing saved); no ncu capture of this launch")
+    if "svr_dense_eval" in kms:
+        calls, ms = kms["svr_dense_eval"]
+        r = _roof("svr_dense_eval", ms, calls, "tensor", fwd_flops, peaks, None,
+                  "box kernel (csrc/fused_query_box.cu): lattice generated in-kernel, 32^3 / 16^3 / 8^3 levels interpolated on the tensor cores "
+                  "from voxel boxes staged in shared memory, nothing saved")
+        t, src = _ncu_traffic("fused_query_kernel(FqParams", files=("r2b_dense_box.txt",))
+        if t is not None:
+            # the capture is one launch over a 64-plane slab of a 256^3 lattice (4.19 M points); scaled to the points of one launch here
+            r["traffic"] = t * (M / max(calls, 1.0)) / (64 * 256 * 256)
+            r["traffic_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum of a 64-plane slab launch, ncu --set full ({src}), scaled by points per launch"
+        out.append(r)
     add("svr_decoder_bwd_fused", "tensor", M * 2 * (2583 * 256 + 2 * 256 * 256), peaks, "fused_bwd_kernel", "dz1, dz0, dfeat in one kernel")
     if "svr_gemm_tn" in kms:
         calls, ms = kms["svr_gemm_tn"]
