@@ -66,22 +66,51 @@ int scratch_alloc(void **ptr, size_t bytes, cudaStream_t st) {
     return 0;
 }
 
-int make_tmap_bf16_sw128(TensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) == alignof(CUtensorMap), "TensorMap layout");
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                  CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;   // resolved through the runtime: no link-time libcuda dependency
+
+static TmapEncodeFn tmap_encoder() {   // resolved through the runtime: no link-time libcuda dependency
+    static TmapEncodeFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
         if (e != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
             set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
-            return -1;
+            return nullptr;
         }
-        encode = (EncodeFn)fn;
+        encode = (TmapEncodeFn)fn;
     }
+    return encode;
+}
+
+int make_tmap_vol_bf16(TensorMap *out, const void *base, int B, int D, int H, int W, int C, int box_x) {
+    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) == alignof(CUtensorMap), "TensorMap layout");
+    TmapEncodeFn encode = tmap_encoder();
+    if (!encode) return -1;
+    if (((uintptr_t)base & 15) || C % 64 || box_x < 1 || box_x > 256) {
+        set_error("volume tensor map: base must be 16-byte aligned and C a multiple of 64 (C=%d)", C);
+        return -1;
+    }
+    const cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    const cuuint64_t gstride[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+    const cuuint32_t box[5] = {64, (cuuint32_t)box_x, 1, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode((CUtensorMap *)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (5-D volume) failed with CUresult %d (B=%d D=%d H=%d W=%d C=%d box_x=%d)", (int)r, B, D, H, W, C, box_x);
+        return -1;
+    }
+    return 0;
+}
+
+int make_tmap_bf16_sw128(TensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) == alignof(CUtensorMap), "TensorMap layout");
+    TmapEncodeFn encode = tmap_encoder();
+    if (!encode) return -1;
     if (((uintptr_t)base & 15) || (ld * 2) % 16 || cols % 64 || box_rows < 1 || box_rows > 256) {
         set_error("tensor map: base must be 16-byte aligned, ld*2 a multiple of 16, cols a multiple of 64 (ld=%lld cols=%lld)", (long long)ld,
                   (long long)cols);

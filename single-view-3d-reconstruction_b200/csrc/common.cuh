@@ -65,6 +65,9 @@ struct alignas(64) TensorMap {
 // row-major bf16 matrix (rows x cols, leading dimension ld elements) tiled in boxes of box_rows x 64 columns
 // with the 128-byte swizzle the UMMA K-major operand layout uses.  0 on success.
 int make_tmap_bf16_sw128(TensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+// channel-last bf16 volume (B, D, H, W, C), C % 64 == 0, as a 5-D tensor (C, W, H, D, B) tiled in boxes of 64 channels x box_x
+// voxels of one x-line, 128-byte swizzle (rows of an MN-major UMMA operand); out-of-volume voxels read as zeros.  0 on success.
+int make_tmap_vol_bf16(TensorMap *out, const void *base, int B, int D, int H, int W, int C, int box_x);
 
 // small POD passed by value to kernels
 struct Dims3 {

@@ -616,11 +616,12 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
 static long long *g_fq_trace = nullptr;
 // 0: every level gathered on the CUDA cores (this file's kernel).  1 (default): the dense evaluator runs the box kernel
 // (fused_query_box.cu: coarse levels interpolated on the tensor cores from voxel boxes staged in shared memory).
-// 2: explicit query points take the box kernel too when they come with the sort-cell table.
+// 2: explicit query points take the box kernel too when they come with the sort-cell table.  3: like 1, voxel boxes staged
+// by cp.async instead of TMA tensor copies (ablation).
 static int g_fq_interp = 1;
 
 namespace fqb {
-void set_interp(int on);
+void set_interp(int on, int tma);
 void set_trace(long long *buf, int block);
 int query_fwd(const float *points, const int *perm, const int *cell_start, int B, int N, const float *x0,
               const uint16_t *const *vols_host, const uint16_t *const *halo_vols_host, const svr_pyramid *pyr_host,
@@ -666,8 +667,8 @@ int svr_debug_fq_trace_block(int block) {
 }
 
 int svr_debug_fq_interp(int mode) {
-    g_fq_interp = mode;
-    fqb::set_interp(mode != 0);
+    g_fq_interp = mode == 3 ? 1 : mode;
+    fqb::set_interp(mode != 0, mode != 3);
     return 0;
 }
 

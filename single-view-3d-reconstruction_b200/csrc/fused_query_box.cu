@@ -64,6 +64,11 @@ constexpr int FQ_VBOX_BYTES = 48 * 1024;         // voxel boxes of the tensor-co
 constexpr int FQ_KMAX = 256;                     // largest voxel box (K of the interpolation product)
 constexpr int FQ_HDR_BYTES = 1280;                // per-tile header (double buffered)
 constexpr int FQ_MAX_ROUNDS = 32, FQ_MAX_CHUNKS = 64;
+// TMA staging of the voxel boxes: one tensor copy per (y, z) line of a box = box_x voxels x 64 channels, 128B-swizzled rows
+// in box order.  The line length is fixed per tensor map; the smallest of a few pre-encoded ones that covers the box is used
+// and becomes the box's x stride.
+constexpr int FQ_TMA_LEVELS = 3, FQ_TMA_NBX = 5;
+__host__ __device__ constexpr int fq_tma_bx(int i) { return i == 0 ? 3 : (i == 1 ? 4 : (i == 2 ? 5 : (i == 3 ? 6 : 8))); }
 // Shared memory is kept SMALL on purpose: what a CTA does not request stays L1 data cache (228 KB - shared memory per SM),
 // and the gather lives on L1 hits -- neighbouring (spatially sorted) rows and the 7 stencil points of a row read the same
 // voxels.  Staging the corner loads through shared memory (cp.async, one 128-byte slot per thread: latency fully hidden, no
@@ -100,6 +105,7 @@ struct TileHdr {
     int bx0[SVR_MAX_LEVELS], by0[SVR_MAX_LEVELS], bz0[SVR_MAX_LEVELS];   // voxel box origin
     int nx[SVR_MAX_LEVELS], ny[SVR_MAX_LEVELS], nvox[SVR_MAX_LEVELS];    // box extent (x, y) and voxel count
     int voff[SVR_MAX_LEVELS];      // byte offset of the level's box in the box arena
+    int nz[SVR_MAX_LEVELS], bxi[SVR_MAX_LEVELS];   // box extent (z); tensor map index of the box's lines (-1: staged by cp.async)
     uint8_t gk[FQ_MAX_CHUNKS];     // K chunks produced by the gather, ascending
     uint8_t rl[FQ_MAX_ROUNDS];     // rounds: level << 4 | stencil point
     uint8_t ops[FQ_MAX_CHUNKS + 2 * FQ_MAX_ROUNDS];   // the tile's schedule: FQ_OP_* << 6 | index into gk / rl
@@ -127,6 +133,8 @@ struct FqParams {
     FqVols halo;                // optional halo'd copies of the wide levels (null entries: generic path)
     int wide_level0;            // first level taken by the wide path (== P.n_levels: none); every level from here on is wide
     int tc_enable;              // tensor-core interpolation of the wide levels whose voxel box fits
+    int use_tma;                // the voxel boxes are staged by TMA tensor copies (else cp.async)
+    TensorMap tmap[FQ_TMA_LEVELS][FQ_TMA_NBX];   // per wide level (index l - wide_level0) and x-line length FQ_TMA_BX[i]
     Pyr P;
     const uint8_t *w0_img, *w1_img, *w2_img;   // pre-swizzled chunk images (svr_pack_decoder_images)
     const float *b0, *b1, *b2, *wout, *bout;
@@ -314,7 +322,7 @@ constexpr int WS2_C = 128, WS2_Y = 18 * 128, WS2_Z = 18 * 18 * 128;
 constexpr int WS3_C = 128, WS3_Y = 10 * 128, WS3_Z = 10 * 10 * 128;
 
 
-__global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqParams p, int64_t n_tiles_host) {
+__global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const __grid_constant__ FqParams p, int64_t n_tiles_host) {
     extern __shared__ uint8_t smem_raw[];
     const FqSmem s = fq_carve(smem_raw, p.nb);
     const int NB = p.nb;
@@ -350,6 +358,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc(s.tmem_ptr, 512);
+    for (int i = threadIdx.x; i < FQ_VBOX_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s.vbox)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
     for (int u = threadIdx.x; u < KC0 * 8; u += blockDim.x) s.utab[u] = pack_unit(p.P, u);
     for (int i = threadIdx.x; i < 4 * FQ_HID; i += blockDim.x) {
         const float *src = i < FQ_HID ? p.b0 : (i < 2 * FQ_HID ? p.b1 : (i < 3 * FQ_HID ? p.b2 : p.wout));
@@ -463,8 +473,15 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
                     lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
                     hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
                 }
-                const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+                int nx = hi[0] - lo[0] + 1;
+                const int ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
                 if (lo[0] > hi[0] || nx > FQ_KMAX || ny > FQ_KMAX || nz > FQ_KMAX) continue;
+                int bxi = -1;                                   // tensor map of the box's lines (its line length = x stride of the box)
+                if (p.use_tma && l - p.wide_level0 < FQ_TMA_LEVELS) {
+                    for (int i = FQ_TMA_NBX - 1; i >= 0; --i)
+                        if (fq_tma_bx(i) >= nx) bxi = i;
+                    if (bxi >= 0) nx = fq_tma_bx(bxi);
+                }
                 const int nvox = nx * ny * nz, C = p.P.C[l];
                 const int bytes = ((nvox + 15) & ~15) * C * 2;
                 if (nvox > FQ_KMAX || C > 128 || voff + bytes > FQ_VBOX_BYTES || nR + 7 > FQ_MAX_ROUNDS) continue;
@@ -477,6 +494,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
                     hdr->ny[l] = ny;
                     hdr->nvox[l] = nvox;
                     hdr->voff[l] = voff;
+                    hdr->bxi[l] = bxi;
+                    hdr->nz[l] = nz;
                 }
                 if (lane < 7) {
                     hdr->rl[nR + lane] = (uint8_t)(l << 4 | lane);
@@ -522,6 +541,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
             if (lane == 0) fq_trace(p, 3, tn, 50);
             // ---- stage the voxel boxes of this tile (cp.async, zero rows up to a multiple of 16)
             if (it > 0) mbar_wait(s.vbox_free, (uint32_t)(it - 1) & 1);     // the previous tile's interpolation products are done
+            uint32_t tma_bytes = 0;
             if (tc_mask) {
                 const int scene = smin;
                 for (int l = p.wide_level0; l < p.P.n_levels; ++l) {
@@ -529,8 +549,21 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
                     const int C = p.P.C[l], W = p.P.W[l], H = p.P.H[l], D = p.P.D[l];
                     const int ncg = C >> 3, nvox = hdr->nvox[l], rows16 = (nvox + 15) & ~15;
                     const int nx = hdr->nx[l], ny = hdr->ny[l], bx0 = hdr->bx0[l], by0 = hdr->by0[l], bz0 = hdr->bz0[l];
-                    const __nv_bfloat16 *vol = p.vols.v[l] + (int64_t)scene * D * H * W * C;
                     const uint32_t dst0 = smem_u32(s.vbox + hdr->voff[l]);
+                    const int bxi = hdr->bxi[l];
+                    if (bxi >= 0) {
+                        // one tensor copy per (y, z) line and 64-channel slab: nx voxels x 128 B, rows in box order; voxels beyond
+                        // the volume's x extent are zero-filled (their weights are zero too)
+                        const int nz = hdr->nz[l], lines = ny * nz, slabs = C >> 6;
+                        tma_bytes += (uint32_t)(lines * slabs * nx * 128);
+                        const TensorMap *tm = &p.tmap[l - p.wide_level0][bxi];
+                        for (int i = lane; i < lines * slabs; i += 32) {
+                            const int sl = i / lines, ln = i - sl * lines, lz = ln / ny, ly = ln - lz * ny;
+                            tma_load_5d(dst0 + sl * (rows16 * 128) + ln * nx * 128, tm, sl * 64, bx0, by0 + ly, bz0 + lz, scene, s.vbox_full);
+                        }
+                        continue;
+                    }
+                    const __nv_bfloat16 *vol = p.vols.v[l] + (int64_t)scene * D * H * W * C;
                     const float inv_ncg = 1.0f / (float)ncg, inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
                     for (int i = lane; i < rows16 * ncg; i += 32) {
                         // small-integer divisions through exact float reciprocals (operands < 2^13)
@@ -547,7 +580,10 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const FqPara
             cp_async_wait<0>();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s.vbox_full);
+            if (lane == 0) {
+                if (tma_bytes) mbar_arrive_expect_tx(s.vbox_full, tma_bytes);
+                else mbar_arrive(s.vbox_full);
+            }
             if (lane == 0) fq_trace(p, 3, tn, 51);
         }
     } else if (warp >= 6 && warp < FQ_PREP_WARP) {
@@ -1062,9 +1098,13 @@ static int fq_fill(FqParams &p, const float *x0, const uint16_t *const *vols_hos
 static long long *g_fq_trace = nullptr;
 static int g_fq_trace_block = 0;
 static int g_fq_interp = 1;     // 0: the coarse levels are gathered on the CUDA cores like the others (ablation)
-void set_interp(int on) { g_fq_interp = on; }
+static int g_fq_tma = 1;        // 0: voxel boxes staged by cp.async instead of TMA tensor copies (ablation)
+void set_interp(int on, int tma) {
+    g_fq_interp = on;
+    g_fq_tma = tma;
+}
 
-static int fq_launch(FqParams &p, int64_t n_tiles, cudaStream_t st) {
+static int fq_launch(FqParams &p, int64_t n_tiles, int n_scenes, cudaStream_t st) {
     static DeviceOnce once;
     int dev;
     if (once.needed(dev)) {
@@ -1078,6 +1118,14 @@ static int fq_launch(FqParams &p, int64_t n_tiles, cudaStream_t st) {
     p.trace_block = g_fq_trace_block;
     p.nb = FQ_NB;
     p.tc_enable = (g_fq_interp && p.wide_level0 + 4 >= p.P.n_levels) ? 1 : 0;    // the box pass covers up to four wide levels
+    p.use_tma = 0;
+    if (p.tc_enable && g_fq_tma) {
+        p.use_tma = 1;
+        for (int l = p.wide_level0; l < p.P.n_levels && l - p.wide_level0 < FQ_TMA_LEVELS && p.use_tma; ++l)
+            for (int i = 0; i < FQ_TMA_NBX && p.use_tma; ++i)
+                if (make_tmap_vol_bf16(&p.tmap[l - p.wide_level0][i], p.vols.v[l], n_scenes, p.P.D[l], p.P.H[l], p.P.W[l], p.P.C[l], fq_tma_bx(i)))
+                    p.use_tma = 0;      // (the cp.async path needs no descriptors)
+    }
     fused_query_kernel<<<grid, FQ_THREADS, fq_smem(FQ_NB), st>>>(p, n_tiles);
     SVR_LAUNCH_CHECK();
     return 0;
@@ -1119,7 +1167,7 @@ int query_fwd(const float *points, const int *perm, const int *cell_start, int B
         p.tiles = (const StTile *)((uint8_t *)scratch + 16);
         p.n_tiles_dev = (const int *)scratch;
     }
-    const int rc = fq_launch(p, n_tiles, st);
+    const int rc = fq_launch(p, n_tiles, B, st);
     if (scratch) SVR_CUDA(cudaFreeAsync(scratch, st));
     return rc;
 }
@@ -1150,7 +1198,7 @@ int dense_eval(int scene, int B, const float *x0, const uint16_t *const *vols_ho
         // (coordinates still use the full sx through lin_coord's n argument)
         SVR_REQUIRE((x_end - x_begin) % BRICK_X == 0, "dense_eval: slab length must be a multiple of %d unless it ends the lattice", BRICK_X);
     }
-    return fq_launch(p, (int64_t)p.bx * p.by * p.bz, as_stream(stream));
+    return fq_launch(p, (int64_t)p.bx * p.by * p.bz, B, as_stream(stream));
 }
 
 }  // namespace fqb

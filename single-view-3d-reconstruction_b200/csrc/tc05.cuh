@@ -79,6 +79,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap,
                  "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+// 5-D tile (coordinates innermost first); elements outside the tensor are zero-filled
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const void *tmap, int c0, int c1, int c2, int c3, int c4, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst_smem),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, uint32_t src_smem) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1)
                  : "memory");

@@ -280,20 +280,21 @@ def test_sorted_aggregated_backward_matches_direct():
     assert _rel_l2(b[4], a[4]) < 1e-4 and _rel_l2(b[5], a[5]) < 1e-4
 
 
-@pytest.mark.parametrize("kernel", ["gather", "box"])
+@pytest.mark.parametrize("kernel", ["gather", "box", "box-cpasync"])
 def test_fused_dense_evaluator_matches_chunked_query(kernel):
     """svr_dense_eval (lattice generated in-kernel, brick order) against the chunked point path on the
     same make_3d_grid points, incl. non-multiple-of-brick sizes, several scenes and an x-slab.  The gather kernel
     (svr_debug_fq_interp(0)) runs the arithmetic of the point path: 1e-5.  The box kernel (default) interpolates the
     coarse levels on the tensor cores with bf16 trilinear weights: 2e-4 on the occupancy probabilities here (the 1e-2
-    bound on the logits against the reference is tests/test_gpu_parity_r2.py::test_dense_eval_256cube_slab_vs_c_oracle)."""
+    bound on the logits against the reference is tests/test_gpu_parity_r2.py::test_dense_eval_256cube_slab_vs_c_oracle);
+    its voxel boxes are staged by TMA tensor copies ("box") or by cp.async ("box-cpasync", svr_debug_fq_interp(3))."""
     import svr_b200
     from svr_b200 import _abi
     sd = R.synthetic_state_dict(31, 128)
     net = _net(128, sd).eval()
     g = torch.Generator().manual_seed(12)
     x = (torch.rand((2, 1, 32, 24, 16), generator=g) < 0.15).float().cuda()
-    _abi.load().svr_debug_fq_interp(0 if kernel == "gather" else 1)
+    _abi.load().svr_debug_fq_interp({"gather": 0, "box": 1, "box-cpasync": 3}[kernel])
     try:
         for lattice in ((19, 10, 7), (32, 24, 16)):
             dense = net.evaluate_grid(x, lattice)

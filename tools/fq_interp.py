@@ -52,13 +52,12 @@ for c0 in range(0, kp, 64 * 7):
     print(f"  cols {c0:5d}..: rel L2 {float((fa[:, sl] - fb[:, sl]).norm() / fa[:, sl].norm().clamp_min(1e-20)):.3e}")
 for i in range(3):
     print(f"saved h{i} rel L2:", float((a[3][i].float() - b[3][i].float()).norm() / a[3][i].float().norm()))
-# dense evaluation, one scene, 256^3 lattice
-for interp in (0, 1):
+# dense evaluation, one scene, 256^3 lattice: gather kernel (0), box kernel with TMA-staged boxes (1), with cp.async-staged boxes (3)
+for interp in (0, 1, 3):
     lib.svr_debug_fq_interp(interp)
     with torch.no_grad():
         g = net.evaluate_grid(x[:1], (256, 256, 256))
     torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _abi.PROFILE.reset(with_events=True)
     with torch.no_grad():
         g = net.evaluate_grid(x[:1], (256, 256, 256))
@@ -67,5 +66,6 @@ for interp in (0, 1):
     res[("d", interp)] = g.clone()
     print(f"interp={interp}: dense 256^3 scene {sum(a.elapsed_time(b) for a, b in ev):.2f} ms", flush=True)
     _abi.PROFILE.reset()
-print("dense max|d|:", float((res[("d", 0)] - res[("d", 1)]).abs().max()))
+print("dense max|d| box(TMA) vs gather:", float((res[("d", 0)] - res[("d", 1)]).abs().max()),
+      " box(TMA) vs box(cp.async):", float((res[("d", 1)] - res[("d", 3)]).abs().max()))
 lib.svr_debug_fq_interp(1)
