@@ -227,7 +227,7 @@ int svr_query_fwd_fused(const float *points, const int *perm, const int *cell_st
  * cores from a box staged in shared memory (bf16 trilinear weights) instead of gathered corner by corner.  2: explicit
  * points with a sort-cell table take the box kernel too (slower than the gather kernel at 50k points per scene: the
  * tiles cut at cell-group boundaries are 77 % full).  3: like 1 with the voxel boxes staged by cp.async instead of TMA
- * tensor copies (ablation).                                                                                  */
+ * tensor copies (ablation); 4: like 2 with cp.async staging.                                                 */
 int svr_debug_fq_interp(int mode);
 /* debug: the block whose timeline svr_debug_fq_trace records (default 0) */
 int svr_debug_fq_trace_block(int block);

@@ -667,8 +667,8 @@ int svr_debug_fq_trace_block(int block) {
 }
 
 int svr_debug_fq_interp(int mode) {
-    g_fq_interp = mode == 3 ? 1 : mode;
-    fqb::set_interp(mode != 0, mode != 3);
+    g_fq_interp = mode == 3 ? 1 : (mode == 4 ? 2 : mode);     // 4: like 2 with cp.async staging
+    fqb::set_interp(mode != 0, mode != 3 && mode != 4);
     return 0;
 }
 

@@ -14,7 +14,7 @@ B, N, D = 1, 4096, 64
 x = (torch.rand(B, 1, D, D, D) < 0.05).float().cuda()
 pts = ((torch.rand(B, N, 3) - 0.5) * 1.03).cuda()
 outs = []
-for mode in (0, 2):
+for mode in (0, 4, 2):
     lib.svr_debug_fq_interp(mode)
     with torch.no_grad():
         vols = net.ifnet_feature_extractor.encode(x)
