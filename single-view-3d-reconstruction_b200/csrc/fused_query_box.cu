@@ -79,7 +79,7 @@ __host__ __device__ constexpr int fq_tma_bx(int i) { return i == 0 ? 3 : (i == 1
 // exception: they REPLACE the L1 traffic of the levels they serve.
 constexpr int fq_smem(int nb) {
     return 1024 + FQ_NA * FQ_A_BYTES + nb * FQ_B_BYTES + FQ_VBOX_BYTES + FQ_BIAS_BYTES + 2 * FQ_TILE * 16 + 512 + FQ_UTAB * 4 + FQ_WGEO_BYTES +
-           2 * FQ_HDR_BYTES + 256 + FQ_TILE * 4;
+           2 * FQ_HDR_BYTES + 256 + FQ_TILE * 4 + 2 * FQ_TMA_LEVELS * FQ_TILE * 16;
 }
 static_assert(fq_smem(FQ_NB) <= 227 * 1024, "fused query shared memory");
 
@@ -227,6 +227,7 @@ struct FqSmem {
     TileHdr *hdr;                // [2]
     int *box;                    // spare
     float *dot;                  // [128] partial fc_out dot products of the second epilogue half
+    float4 *ctr;                 // [2][FQ_TMA_LEVELS][128] unnormalised sample position (x, y, z) of the stencil centre per wide level
 };
 
 __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw, int nb) {
@@ -259,6 +260,7 @@ __device__ __forceinline__ FqSmem fq_carve(uint8_t *raw, int nb) {
     s.hdr = (TileHdr *)((uint8_t *)s.wgeo + FQ_WGEO_BYTES);
     s.box = (int *)((uint8_t *)s.hdr + 2 * FQ_HDR_BYTES);
     s.dot = (float *)((uint8_t *)s.box + 256);
+    s.ctr = (float4 *)((uint8_t *)s.dot + FQ_TILE * 4);
     return s;
 }
 
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const __grid
             // ---- voxel boxes of the wide levels: the extreme corners of a row come from the -/+ displaced samples (the
             // index arithmetic of stencil_corners), reduced over the warp; lane 0 then writes the schedule
             int tc_mask = 0, voff = 0, nR = 0, nG = 0;
-            for (int l = p.wide_level0; l < p.P.n_levels; ++l) {
+            for (int l = p.wide_level0; l < p.P.n_levels && l - p.wide_level0 < FQ_TMA_LEVELS; ++l) {
                 if (!p.tc_enable || !one_scene) break;
                 int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
                 const int size[3] = {p.P.W[l], p.P.H[l], p.P.D[l]};
@@ -535,6 +537,19 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const __grid
                 hdr->nG = nG;
                 hdr->nR = nR;
                 hdr->pad_[0] = smin;
+            }
+            // unnormalised sample positions of the stencil centre on the tensor-core interpolated levels: the producers need
+            // them in every round, and the index arithmetic was half of what a round cost them
+            for (int l = p.wide_level0; l < p.P.n_levels && l - p.wide_level0 < FQ_TMA_LEVELS; ++l) {
+                if (!((tc_mask >> l) & 1)) continue;
+                const float fw = (float)p.P.W[l], fh = (float)p.P.H[l], fd = (float)p.P.D[l];
+                float4 *dst = s.ctr + ((it & 1) * FQ_TMA_LEVELS + (l - p.wide_level0)) * FQ_TILE;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 q = pts_s[lane + 32 * j];
+                    dst[lane + 32 * j] = make_float4(unnorm(__fmul_rn(2.0f, q.z), fw, p.P.align), unnorm(__fmul_rn(2.0f, q.y), fh, p.P.align),
+                                                     unnorm(__fmul_rn(2.0f, q.x), fd, p.P.align), 0.f);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(s.hdr_full + (it & 1));
@@ -702,8 +717,31 @@ __global__ void __launch_bounds__(FQ_THREADS, 1) fused_query_kernel(const __grid
                 const int r = wg * 8 + (lane >> 2), qd = lane & 3, bb = qd & 1, e = qd >> 1;
                 const float4 pq = pts_s[r];
                 const bool rv = __float_as_int(pq.w) >= 0;
+                // the corners of stencil_corners(p.P, l, d, ...): centre positions from the prep warp's table, only the displaced
+                // axis is re-evaluated (same operations, same bits)
                 Corners c;
-                stencil_corners(p.P, l, d, pq.x, pq.y, pq.z, c);
+                {
+                    const WideGeo &G = s.wgeo[l];
+                    const float4 ct = s.ctr[((it & 1) * FQ_TMA_LEVELS + (l - p.wide_level0)) * FQ_TILE + r];
+                    float ix = ct.x, iy = ct.y, iz = ct.z;
+                    if (d != 0) {
+                        const float sgn = (d & 1) ? -p.P.delta : p.P.delta;
+                        if (d <= 2) ix = unnorm(__fadd_rn(__fmul_rn(2.0f, pq.z), sgn), G.fw, p.P.align);
+                        else if (d <= 4) iy = unnorm(__fadd_rn(__fmul_rn(2.0f, pq.y), sgn), G.fh, p.P.align);
+                        else iz = unnorm(__fadd_rn(__fmul_rn(2.0f, pq.x), sgn), G.fd, p.P.align);
+                    }
+                    const float fx = fminf(fmaxf(floorf(ix), -4.0f), G.fw + 2.0f), fy = fminf(fmaxf(floorf(iy), -4.0f), G.fh + 2.0f),
+                                fz = fminf(fmaxf(floorf(iz), -4.0f), G.fd + 2.0f);
+                    c.x0 = (int)fx;
+                    c.y0 = (int)fy;
+                    c.z0 = (int)fz;
+                    c.wx[1] = ix - fx;
+                    c.wx[0] = (fx + 1.0f) - ix;
+                    c.wy[1] = iy - fy;
+                    c.wy[0] = (fy + 1.0f) - iy;
+                    c.wz[1] = iz - fz;
+                    c.wz[0] = (fz + 1.0f) - iz;
+                }
                 const int nvox = hdr->nvox[l], nkc = (nvox + 63) >> 6;
                 const int y = c.y0 + bb, z = c.z0 + e;
                 const bool yz_ok = rv && y >= 0 && y < p.P.H[l] && z >= 0 && z < p.P.D[l];
