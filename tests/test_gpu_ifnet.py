@@ -310,6 +310,28 @@ def test_fused_dense_evaluator_matches_chunked_query(kernel):
         _abi.load().svr_debug_fq_interp(1)
 
 
+@pytest.mark.parametrize("dims,lattice", [((70, 52, 56), (140, 104, 112)), ((48, 80, 64), (48, 80, 64)), ((64, 64, 64), (193, 67, 131))])
+def test_box_kernel_dense_evaluator_odd_shapes(dims, lattice):
+    """Dense evaluator, box kernel against gather kernel on non-cubic / non-power-of-two scenes (the reference's production
+    grids are (139,104,112) and (70,52,56), trainer_scene_net.py:30-31) and lattices that are not multiples of the brick:
+    box extents, tensor-map line lengths and the per-tile schedule all vary from tile to tile."""
+    from svr_b200 import _abi
+    sd = R.synthetic_state_dict(35, 128)
+    net = _net(128, sd).eval()
+    g = torch.Generator().manual_seed(14)
+    x = (torch.rand((1, 1, *dims), generator=g) < 0.1).float().cuda()
+    out = {}
+    try:
+        for mode in (0, 1, 3):
+            _abi.load().svr_debug_fq_interp(mode)
+            out[mode] = net.evaluate_grid(x, lattice)
+            torch.cuda.synchronize()
+    finally:
+        _abi.load().svr_debug_fq_interp(1)
+    assert float((out[1] - out[0]).abs().max()) < 2e-4
+    assert float((out[3] - out[0]).abs().max()) < 2e-4
+
+
 def test_box_kernel_on_sorted_points_matches_gather_kernel():
     """The box kernel on explicit (sorted) query points -- svr_debug_fq_interp(2): row tiles cut at sort-cell group
     boundaries, 16^3 / 8^3 levels interpolated on the tensor cores -- against the gather kernel on a 128^3 scene pair
