@@ -416,8 +416,10 @@ class Ctx:
             self.clocks.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        self.host_enqueue_ms = (time.perf_counter() - t0) * 1e3 / max(steps, 1)    # host time to ENQUEUE one step (no sync inside)
         e1.record()
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1))
@@ -460,7 +462,8 @@ def run_config2(ctx):
     torch.backends.cudnn.benchmark = os.environ.get("SVR_CUDNN_BENCHMARK", "1") == "1"   # reference: trainer_ifnet.py:64
     torch.manual_seed(0)
     net = svr_b200.IFNet().to(dev).train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+    use_graph = os.environ.get("SVR_GRAPH", "1") == "1" and not args.profile_mode
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     reducer = svr_dist.GradReducer(net) if world > 1 else None
     x, pts_h, occ_h = synthetic_inputs(SCENES_PER_GPU, 100 + rank, dev)
     pts, occ = pts_h.to(dev), occ_h.to(dev)
@@ -477,8 +480,25 @@ def run_config2(ctx):
         opt.step()
         return loss
 
+    eager_step = step
     for _ in range(max(args.warmup, 3)):
         step(x, pts, occ)
+    # The whole step (forward, loss, backward, gradient all-reduce, Adam) as ONE CUDA graph (svr_b200.GraphedStep): the
+    # host needs most of the step's duration to enqueue its ~160 launches, and eight ranks share one host.  SVR_GRAPH=0
+    # runs the step eagerly; a capture that fails falls back to it.
+    graph_note, launches_per_step = "eager (SVR_GRAPH=0 or --profile-mode)", None
+    if use_graph:
+        try:
+            ctx.abi.PROFILE.reset(with_events=False)
+            gstep = svr_b200.GraphedStep(eager_step, (x, pts, occ), warmup=0)
+            launches_per_step = ctx.abi.PROFILE.total_launches()       # counted while the step was recorded
+            step = gstep
+            graph_note = "whole step replayed as one CUDA graph (svr_b200.GraphedStep)"
+            for _ in range(2):
+                step(x, pts, occ)
+        except Exception as e:      # noqa: BLE001
+            graph_note = f"eager: graph capture failed ({type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
     # ---------------- timed: device-resident inputs
     ctx.abi.PROFILE.reset(with_events=False)
     if args.profile_mode:
@@ -488,7 +508,8 @@ def run_config2(ctx):
     if args.profile_mode:
         torch.cuda.profiler.stop()
     clk = ctx.clocks.stop() if rank == 0 else None
-    launches = ctx.abi.PROFILE.total_launches()
+    launches = ctx.abi.PROFILE.total_launches() if launches_per_step is None else launches_per_step * args.steps
+    host_ms = ctx.max_over_ranks(ctx.host_enqueue_ms)
     value = world * n_pts_step * args.steps / (ms * 1e-3)
     if args.profile_mode:
         if rank == 0:
@@ -535,7 +556,7 @@ def run_config2(ctx):
     ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    kms = ctx.kernel_pass(lambda i: step(x, pts, occ), prof_steps)
+    kms = ctx.kernel_pass(lambda i: eager_step(x, pts, occ), prof_steps)      # eager: CUDA events between the launches
     e1.record()
     torch.cuda.synchronize()
     step_ms_prof = e0.elapsed_time(e1) / prof_steps
@@ -545,7 +566,7 @@ def run_config2(ctx):
         roofs, hot = query_rooflines(kms, peaks, n_pts_step, SCENES_PER_GPU)
         roofs.sort(key=lambda r: -r["ms_per_step"])
         line = base_line(ctx, 2, value, ms, args.steps)
-        line.update({"clocks": clk, "gpu_launches": launches,
+        line.update({"clocks": clk, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "step_mode": graph_note,
                      "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                              "how": "public API (svr_b200.IFNet + HostPrefetcher): every step's inputs are copied from pinned host memory inside "
                                     "the timed region (the copy of step i+1 overlaps step i) and every step's loss is read back (async D2H, "

@@ -8,6 +8,7 @@ from .model.ifnet import (IFNet, IFNetFeatureExtractor, IFNetFeatureExtractor128
                           implicit_to_mesh, make_3d_grid)
 from .model.projection import project  # noqa: F401
 from .prefetch import HostPrefetcher  # noqa: F401
+from .graph import GraphedStep  # noqa: F401
 
 __all__ = ["IFNet", "IFNetFeatureExtractor", "IFNetFeatureExtractor128", "configure", "evaluate_network_on_grid",
-           "implicit_to_mesh", "make_3d_grid", "project", "ops", "HostPrefetcher"]
+           "implicit_to_mesh", "make_3d_grid", "project", "ops", "HostPrefetcher", "GraphedStep"]

@@ -19,7 +19,15 @@ def _lib():
     return _abi.load()
 
 
+try:      # raw handle of the current stream of the current device: ~0.3 us instead of ~16 us through torch.cuda.current_stream()
+    _raw_stream, _cur_device = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+except Exception:                                            # pragma: no cover (older / newer torch without the private hooks)
+    _raw_stream = _cur_device = None
+
+
 def _stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -52,6 +60,10 @@ def _entry(fn):
     def wrapper(*args, **kw):
         dev = _cuda_device_of(args)
         if dev is None:
+            return fn(*args, **kw)
+        # fast path (a training step makes ~60 of these calls: the two context managers were 1 ms of host time per step)
+        same_dev = _cur_device is not None and dev.index == _cur_device()
+        if same_dev and not torch.is_autocast_enabled("cuda"):
             return fn(*args, **kw)
         with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
             return fn(*args, **kw)
