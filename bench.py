@@ -556,7 +556,15 @@ def run_config2(ctx):
     ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    kms = ctx.kernel_pass(lambda i: eager_step(x, pts, occ), prof_steps)      # eager: CUDA events between the launches
+    # eager, and with the side-stream overlaps off: a bracket around a kernel that shares the SMs with another stream's
+    # kernels measures the contention, not the kernel (the weight-gradient GEMMs next to the scatter read 1.05 ms instead of 0.42)
+    from svr_b200 import ops as _ops
+    _ov = (_ops.OVERLAP_WGRAD, _ops.OVERLAP_PREP)
+    _ops.OVERLAP_WGRAD = _ops.OVERLAP_PREP = False
+    try:
+        kms = ctx.kernel_pass(lambda i: eager_step(x, pts, occ), prof_steps)
+    finally:
+        _ops.OVERLAP_WGRAD, _ops.OVERLAP_PREP = _ov
     e1.record()
     torch.cuda.synchronize()
     step_ms_prof = e0.elapsed_time(e1) / prof_steps
