@@ -464,7 +464,8 @@ def run_config2(ctx):
     net = svr_b200.IFNet().to(dev).train()
     use_graph = os.environ.get("SVR_GRAPH", "1") == "1" and not args.profile_mode
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True, capturable=use_graph)
-    reducer = svr_dist.GradReducer(net) if world > 1 else None
+    buckets = svr_dist.FINE_BUCKETS if os.environ.get("SVR_BUCKETS", "") == "fine" else None     # experiment switch
+    reducer = svr_dist.GradReducer(net, buckets=buckets) if world > 1 else None
     x, pts_h, occ_h = synthetic_inputs(SCENES_PER_GPU, 100 + rank, dev)
     pts, occ = pts_h.to(dev), occ_h.to(dev)
     x_pin, pts_pin, occ_pin = x.cpu().pin_memory(), pts_h.pin_memory(), occ_h.pin_memory()
