@@ -378,12 +378,28 @@ def evaluate_network_on_grid(network, x, resolution, res_increase=None):
 
 
 def implicit_to_mesh(network, x, resolution, threshold_p, output_path, res_increase=None):
-    """ifnet.py:232-234: marching cubes on 1 - occupancy (CPU, through the reference's own
-    ``util.visualize.visualize_sdf`` when it is importable)."""
-    value_grid = evaluate_network_on_grid(network, x, resolution, res_increase)
+    """ifnet.py:232-234: marching cubes on ``1 - occupancy`` at ``threshold_p``, written as an OBJ file.
+
+    With the reference's ``util.visualize`` importable its ``visualize_sdf`` is called exactly like the reference does
+    (same third-party mesher, same file).  Otherwise the iso-surface is extracted ON THE DEVICE the occupancy grid was
+    computed on (``svr_b200.mesh.marching_cubes``: generated case table, watertight, one vertex per crossed grid edge)
+    and only the mesh is copied to the host -- no 67 MB grid transfer, no CPU marching cubes."""
     try:
         from util.visualize import visualize_sdf  # type: ignore
-    except Exception as e:  # marching_cubes / trimesh are not part of this package
-        raise RuntimeError("implicit_to_mesh needs the reference's util.visualize (marching_cubes) on sys.path; "
-                           "use evaluate_network_on_grid for the occupancy grid") from e
-    visualize_sdf(1 - value_grid, output_path, level=threshold_p)
+    except Exception:  # marching_cubes / trimesh are not part of this package
+        visualize_sdf = None
+    if visualize_sdf is not None:
+        value_grid = evaluate_network_on_grid(network, x, resolution, res_increase)
+        visualize_sdf(1 - value_grid, output_path, level=threshold_p)
+        return
+    from .. import mesh as _mesh
+    if res_increase is None:
+        res_increase = args.inf_res
+    shape = tuple(int(res_increase * int(r)) for r in resolution)
+    with torch.no_grad():
+        if isinstance(network, IFNet) and not network.training and network.fused_available() and x.is_cuda and _precision() != 32:
+            occ = network.evaluate_grid(x, shape, scenes=[0])[0]                 # stays on the device
+        else:
+            occ = torch.from_numpy(evaluate_network_on_grid(network, x, resolution, res_increase)).to(x.device)
+        vertices, triangles = _mesh.marching_cubes(1.0 - occ, float(threshold_p))
+    _mesh.export_obj(vertices, triangles, output_path)
