@@ -613,12 +613,27 @@ def run_config1(ctx):
         with torch.no_grad():
             return net(proj(proj.depthmap_to_normed_points(d, 1)), p)
 
+    eager_step = step
     for _ in range(max(args.warmup, 3)):
         step(depth, pts)
+    # one scene, 50 k points: ~70 launches of a few microseconds each -- the call is launch-bound, so it is recorded once and
+    # replayed as a CUDA graph (svr_b200.GraphedStep; SVR_GRAPH=0: eager)
+    graph_note, launches_per_step = "eager (SVR_GRAPH=0)", None
+    if os.environ.get("SVR_GRAPH", "1") == "1":
+        try:
+            ctx.abi.PROFILE.reset(with_events=False)
+            gstep = svr_b200.GraphedStep(eager_step, (depth, pts), warmup=0)
+            launches_per_step = ctx.abi.PROFILE.total_launches()
+            step = gstep
+            graph_note = "forward replayed as one CUDA graph (svr_b200.GraphedStep)"
+            step(depth, pts)
+        except Exception as e:      # noqa: BLE001
+            graph_note = f"eager: graph capture failed ({type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
     ctx.abi.PROFILE.reset(with_events=False)
     ms = ctx.timed(lambda i: step(depth, pts), args.steps, sample_clocks=True)
     clk = ctx.clocks.stop() if rank == 0 else None
-    launches = ctx.abi.PROFILE.total_launches()
+    launches = ctx.abi.PROFILE.total_launches() if launches_per_step is None else launches_per_step * args.steps
 
     def e2e_step(i):
         out_pin.copy_(step(depth_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True)), non_blocking=True)
@@ -626,13 +641,13 @@ def run_config1(ctx):
 
     e2e_step(0)
     ms_e2e = ctx.timed(e2e_step, args.steps)
-    kms = ctx.kernel_pass(lambda i: step(depth, pts), min(args.steps, 5))
+    kms = ctx.kernel_pass(lambda i: eager_step(depth, pts), min(args.steps, 5))
     if rank == 0:
         peaks = _peaks()
         roofs, _ = query_rooflines(kms, peaks, POINTS, 1, training=False)
         roofs.sort(key=lambda r: -r["ms_per_step"])
         line = base_line(ctx, 1, world * POINTS * args.steps / (ms * 1e-3), ms, args.steps)
-        line.update({"clocks": clk, "gpu_launches": launches,
+        line.update({"clocks": clk, "gpu_launches": launches, "step_mode": graph_note,
                      "e2e": {"value": world * POINTS * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": depth_h.numel() * 4 + pts_h.numel() * 4,
                              "d2h_bytes_per_step": POINTS * 4, "ms_per_step": ms_e2e / args.steps,
                              "how": "project + IFNet.forward through the module API; depth map and points copied from pinned host memory and the "
