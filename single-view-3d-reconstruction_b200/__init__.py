@@ -10,6 +10,7 @@ from .model.projection import project  # noqa: F401
 from .prefetch import HostPrefetcher  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
 from .mesh import export_obj, marching_cubes  # noqa: F401
+from . import data  # noqa: F401
 
 __all__ = ["IFNet", "IFNetFeatureExtractor", "IFNetFeatureExtractor128", "configure", "evaluate_network_on_grid",
            "implicit_to_mesh", "make_3d_grid", "project", "ops", "HostPrefetcher", "GraphedStep", "marching_cubes", "export_obj"]
