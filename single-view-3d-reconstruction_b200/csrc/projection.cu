@@ -143,8 +143,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uin
     const uint32_t *src = in + (size_t)b * stride;
     uint32_t v = 0;
     const int i0 = j * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+    if (i0 + SCAN_PER_THREAD <= n && (stride & 3) == 0) {
+        // 16-byte loads: a thread's 16 entries are one 64-byte line segment (scalar loads issued 16 requests of 32 sectors
+        // each per warp: the two popcount scans of the 256^3 bitmaps took 232 us for 2 x 134 MB)
 #pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; ++k) v += scan_load<MODE>(src, i0 + k, n);
+        for (int k = 0; k < SCAN_PER_THREAD; k += 4) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(src + i0 + k);
+            v += MODE == 0 ? (uint32_t)(__popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w)) : q.x + q.y + q.z + q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; ++k) v += scan_load<MODE>(src, i0 + k, n);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
@@ -183,10 +193,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(const uint32_
     uint32_t *dst = out + (size_t)b * stride;
     const int i0 = j * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
     uint32_t v[SCAN_PER_THREAD], tsum = 0;
+    const bool vec = i0 + SCAN_PER_THREAD <= n && (stride & 3) == 0;
+    if (vec) {
 #pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-        v[k] = scan_load<MODE>(src, i0 + k, n);
-        tsum += v[k];
+        for (int k = 0; k < SCAN_PER_THREAD; k += 4) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(src + i0 + k);
+            v[k] = MODE == 0 ? (uint32_t)__popc(q.x) : q.x;
+            v[k + 1] = MODE == 0 ? (uint32_t)__popc(q.y) : q.y;
+            v[k + 2] = MODE == 0 ? (uint32_t)__popc(q.z) : q.z;
+            v[k + 3] = MODE == 0 ? (uint32_t)__popc(q.w) : q.w;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; ++k) tsum += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+            v[k] = scan_load<MODE>(src, i0 + k, n);
+            tsum += v[k];
+        }
     }
     uint32_t incl = tsum;
 #pragma unroll
@@ -200,10 +224,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(const uint32_
     uint32_t wpre = 0;
     for (int w = 0; w < warp; ++w) wpre += red[w];
     uint32_t run = base_s + wpre + incl - tsum;
+    if (vec) {
 #pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-        if (i0 + k < n) dst[i0 + k] = run;
-        run += v[k];
+        for (int k = 0; k < SCAN_PER_THREAD; k += 4) {
+            uint4 q;
+            q.x = run;
+            q.y = q.x + v[k];
+            q.z = q.y + v[k + 1];
+            q.w = q.z + v[k + 2];
+            run = q.w + v[k + 3];
+            *reinterpret_cast<uint4 *>(dst + i0 + k) = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+            if (i0 + k < n) dst[i0 + k] = run;
+            run += v[k];
+        }
     }
     if (total_out && j == nblk - 1 && threadIdx.x == SCAN_THREADS - 1) total_out[b] = (int)run;
 }
@@ -265,14 +302,17 @@ __global__ void vox_rank_kernel(const float *__restrict__ pts, VoxParams vp, con
     rec[o + s + rank] = make_float4(r[0], r[1], r[2], 0.f);
 }
 
-// 32 bits of a map's bitmap starting at bit index bit0 (may be negative or run past the end: zeros there)
+// The low NEED bits of a map's bitmap starting at bit index bit0 (may be negative or run past the end: zeros there); the
+// bits above them are unspecified.  The second word is only loaded when the NEED bits straddle a word boundary (3 of 32
+// offsets for the 3-bit windows of the accumulate pass, which loaded 18 words per cell before).
+template <int NEED>
 __device__ __forceinline__ uint32_t bitmap_window(const uint32_t *__restrict__ bm, int64_t bit0, int64_t nbits) {
     if (bit0 <= -32 || bit0 >= nbits) return 0u;
     const int64_t w0 = bit0 >> 5;          // floor division (arithmetic shift)
     const int sh = (int)(bit0 & 31);
     const int64_t nw = (nbits + 31) >> 5;
     const uint32_t lo = (w0 >= 0 && w0 < nw) ? bm[w0] : 0u;
-    const uint32_t hi = (sh && w0 + 1 >= 0 && w0 + 1 < nw) ? bm[w0 + 1] : 0u;
+    const uint32_t hi = (sh > 32 - NEED && w0 + 1 >= 0 && w0 + 1 < nw) ? bm[w0 + 1] : 0u;
     return __funnelshift_r(lo, hi, sh);
 }
 
@@ -335,7 +375,7 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
         for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
-                const uint32_t w3 = bitmap_window(bm, (int64_t)cell + dz * s12 + dy * S2 - 1, vp.V) & 7u;
+                const uint32_t w3 = bitmap_window<3>(bm, (int64_t)cell + dz * s12 + dy * S2 - 1, vp.V) & 7u;
                 occ |= w3 << (((dz + 1) * 3 + (dy + 1)) * 3);
             }
         s_cell[tid] = cell;
