@@ -371,13 +371,35 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
         const uint32_t *bm = bitmap + (size_t)b * vp.Wd;
         const int cell = cell_lin[(size_t)b * vp.N + u];
         // occupancy of the neighbourhood: bit ((dz+1)*3 + (dy+1))*3 + (dx+1)
+        const int first = cell - s12 - S2 - 1;
+        if (first >= 0 && (int64_t)cell + s12 + S2 + 34 <= (int64_t)vp.Wd * 32) {
+            // interior cell (all but the first and last two slabs' worth): no range checks, 32-bit indices, the nine
+            // first words loaded back to back
+            uint32_t lo[9], hi[9];
 #pragma unroll
-        for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const uint32_t w3 = bitmap_window<3>(bm, (int64_t)cell + dz * s12 + dy * S2 - 1, vp.V) & 7u;
-                occ |= w3 << (((dz + 1) * 3 + (dy + 1)) * 3);
+            for (int k = 0; k < 9; ++k) {
+                const int bit0 = first + (k / 3) * s12 + (k % 3) * S2;
+                lo[k] = bm[bit0 >> 5];
             }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int bit0 = first + (k / 3) * s12 + (k % 3) * S2;
+                hi[k] = (bit0 & 31) > 29 ? bm[(bit0 >> 5) + 1] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int bit0 = first + (k / 3) * s12 + (k % 3) * S2;
+                occ |= (__funnelshift_r(lo[k], hi[k], bit0 & 31) & 7u) << (k * 3);
+            }
+        } else {
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const uint32_t w3 = bitmap_window<3>(bm, (int64_t)cell + dz * s12 + dy * S2 - 1, vp.V) & 7u;
+                    occ |= w3 << (((dz + 1) * 3 + (dy + 1)) * 3);
+                }
+        }
         s_cell[tid] = cell;
         s_map[tid] = b;
         s_u[tid] = u;
