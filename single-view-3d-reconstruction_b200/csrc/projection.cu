@@ -355,7 +355,8 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
     // single non-isolated cell pay for the general path -- 10 % of the cells at 256^3, a third of the warps' time.)
     __shared__ int s_cell[256], s_map[256], s_u[256];
     __shared__ uint32_t s_occ[256];
-    __shared__ int s_list[2][256], s_wcnt[2][8], s_n[2];
+    __shared__ uint16_t s_list[256 + 2048];        // isolated cells (thread index), then owned voxels (thread index << 3 | sh)
+    __shared__ int s_wcnt[9][8], s_n[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + tid;
     bool valid = t < (int64_t)vp.B * vp.N;
@@ -405,29 +406,73 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
         s_u[tid] = u;
         s_occ[tid] = occ;
     }
+    // Compaction.  List 0: the isolated cells.  Lists 1..8: the voxels (cell, corner shift sh) that a general cell OWNS, shift
+    // by shift -- one entry per voxel that phase C has to sum, so that every lane of a phase-C warp has a voxel (walking
+    // the eight shifts of a cell in one thread left the lanes whose cell does not own the current shift idle: about half
+    // of them), and lanes of a warp mostly share the shift, which bounds the number of sources (8, 4, 4, 2, 4, 2, 2, 1).
     const bool iso = valid && occ == (1u << 13), gen = valid && !iso;
-    const uint32_t m_iso = __ballot_sync(0xffffffffu, iso), m_gen = __ballot_sync(0xffffffffu, gen);
-    if (lane == 0) {
-        s_wcnt[0][warp] = __popc(m_iso);
-        s_wcnt[1][warp] = __popc(m_gen);
+    uint32_t own = 0;                                  // bit sh: no occupied source with a smaller pass index
+    if (gen) {
+#pragma unroll
+        for (int sh = 0; sh < 8; ++sh) own |= (occ & c_vox_lower[sh]) ? 0u : (1u << sh);
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t rank_lo = 0, rank_hi = 0;                 // 9 ranks inside the warp, 6 bits each (<= 31)
+    {
+        const uint32_t m = __ballot_sync(0xffffffffu, iso);
+        if (lane == 0) s_wcnt[0][warp] = __popc(m);
+        rank_lo = __popc(m & lt);
+    }
+#pragma unroll
+    for (int sh = 0; sh < 8; ++sh) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (own >> sh) & 1u);
+        if (lane == 0) s_wcnt[sh + 1][warp] = __popc(m);
+        const uint32_t r = __popc(m & lt);
+        if (sh < 4) rank_lo |= r << (6 * (sh + 1));
+        else rank_hi |= r << (6 * (sh - 4));
     }
     __syncthreads();
-    if (tid < 2) {
-        int acc = 0;
-        for (int w = 0; w < 8; ++w) {
-            const int c = s_wcnt[tid][w];
-            s_wcnt[tid][w] = acc;
-            acc += c;
+    if (warp == 0) {
+        // exclusive scan of the 72 (list, warp) counts in list-major order; the voxel lists share one index space
+        int c[3], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = lane * 3 + k;
+            c[k] = idx < 72 ? s_wcnt[idx >> 3][idx & 7] : 0;
+            tot += c[k];
         }
-        s_n[tid] = acc;
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t2;
+        }
+        int run = incl - tot;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = lane * 3 + k;
+            if (idx < 72) s_wcnt[idx >> 3][idx & 7] = run;
+            run += c[k];
+        }
+        if (lane == 31) s_n[1] = incl;                              // everything: isolated cells + owned voxels
     }
     __syncthreads();
-    if (iso) s_list[0][s_wcnt[0][warp] + __popc(m_iso & ((1u << lane) - 1))] = tid;
-    if (gen) s_list[1][s_wcnt[1][warp] + __popc(m_gen & ((1u << lane) - 1))] = tid;
+    // list 0 occupies [0, n_iso) of the shared index space, the voxel lists follow: n_iso = offset of (list 1, warp 0)
+    if (tid == 0) s_n[0] = s_wcnt[1][0];
+    if (iso) s_list[s_wcnt[0][warp] + (rank_lo & 63u)] = (uint16_t)tid;
+    if (gen) {
+#pragma unroll
+        for (int sh = 0; sh < 8; ++sh)
+            if ((own >> sh) & 1u) {
+                const uint32_t r = sh < 4 ? (rank_lo >> (6 * (sh + 1))) & 63u : (rank_hi >> (6 * (sh - 4))) & 63u;
+                s_list[s_wcnt[sh + 1][warp] + r] = (uint16_t)((tid << 3) | sh);
+            }
+    }
     __syncthreads();
+    const int n_iso = s_n[0], n_all = s_n[1];
     // Phase B: isolated cells -- every one of the 8 voxels has the cell's own run as its only contribution
-    for (int i = tid; i < s_n[0]; i += blockDim.x) {
-        const int e = s_list[0][i], cell = s_cell[e], bb = s_map[e];
+    for (int i = tid; i < n_iso; i += blockDim.x) {
+        const int e = s_list[i], cell = s_cell[e], bb = s_map[e];
         const size_t o = (size_t)bb * vp.N;
         float *gmap = grid + (int64_t)bb * vp.V;
         const int s_own = start[o + s_u[e]], c_own = count[o + s_u[e]];
@@ -445,49 +490,38 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
             gmap[v] = vox_finish(acc[ps], (int64_t)bb * vp.V + v, tail_start, sat_mask);
         }
     }
-    // Phase C: the general case
-    for (int i = tid; i < s_n[1]; i += blockDim.x) {
-        const int e = s_list[1][i], cell = s_cell[e], bb = s_map[e];
+    // Phase C: the voxels owned by general cells, one per thread.  The owner sums every contribution in the reference's
+    // order: the sources are walked as the SET BITS of occ & mask from the highest bit down, which is ascending pass order
+    // (bit index and pass index run opposite ways in every coordinate).  (Round-2 history: a rolled (sh, ps) double loop
+    // per cell spent 87 % of the kernel's instructions on index arithmetic and bit tests (ncu source view); unrolling it
+    // made 36 separate bodies that the lanes of a warp no longer share: 520 -> 870 us.)
+    for (int i = n_iso + tid; i < n_all; i += blockDim.x) {
+        const int ent = s_list[i], e = ent >> 3, sh = ent & 7;
+        const int cell = s_cell[e], bb = s_map[e];
         const uint32_t occ_e = s_occ[e];
         const size_t o = (size_t)bb * vp.N;
         const uint32_t *bm = bitmap + (size_t)bb * vp.Wd;
         const uint32_t *wp = wprefix + (size_t)bb * vp.Wd;
-        float *gmap = grid + (int64_t)bb * vp.V;
-        const int s_own = start[o + s_u[e]], c_own = count[o + s_u[e]];
-        // The rolled (sh, ps) double loop spent ~35 instructions per pair on index arithmetic and bit tests -- 87 % of the
-        // kernel's instructions (ncu source view) -- although only two or three of a voxel's eight possible sources are
-        // occupied.  Now: ownership is one AND with a constant mask (the neighbours of the lower passes), and the sources are
-        // walked as the SET BITS of occ & mask from the highest bit down, which is ascending pass order (bit index and pass
-        // index run opposite ways in every coordinate).  (Unrolling the double loop instead made the 36 bodies separate code
-        // that the differently populated threads of a warp no longer share: 520 -> 870 us.)
-#pragma unroll 1
-        for (int sh = 0; sh < 8; ++sh) {
-            const int sz = (sh >> 2) & 1, sy = (sh >> 1) & 1, sx = sh & 1;
-            if (occ_e & c_vox_lower[sh]) continue;               // an occupied source with a smaller pass index owns the voxel
-            uint32_t srcs = occ_e & c_vox_src[sh];               // includes this cell (bit 13, pass sh)
-            float acc = 0.f;
-            while (srcs) {
-                const int bit = 31 - __clz(srcs);
-                srcs &= ~(1u << bit);
-                const int q9 = (bit * 57) >> 9, r9 = bit - q9 * 9, q3 = (r9 * 11) >> 5;      // bit / 9, bit % 9, (bit % 9) / 3
-                const int nz = q9 - 1, ny = q3 - 1, nx = r9 - q3 * 3 - 1;
-                const int ps = ((sz - nz) << 2) | ((sy - ny) << 1) | (sx - nx);
-                int s0 = s_own, cnt = c_own;
-                if (bit != 13) {
-                    const int id = cell_rank(bm, wp, cell + nz * s12 + ny * S2 + nx);
-                    s0 = start[o + id];
-                    cnt = count[o + id];
-                }
-                for (int q = 0; q < cnt; ++q) {
-                    const float4 rr = __ldg(rec + o + s0 + q);
-                    const float r[3] = {rr.x, rr.y, rr.z};
-                    const float m[3] = {__fsub_rn(1.0f, rr.x), __fsub_rn(1.0f, rr.y), __fsub_rn(1.0f, rr.z)};
-                    acc = __fadd_rn(acc, corner_weight(r, m, ps));
-                }
+        const int sz = (sh >> 2) & 1, sy = (sh >> 1) & 1, sx = sh & 1;
+        uint32_t srcs = occ_e & c_vox_src[sh];               // includes this cell (bit 13, pass sh)
+        float acc = 0.f;
+        while (srcs) {
+            const int bit = 31 - __clz(srcs);
+            srcs &= ~(1u << bit);
+            const int q9 = (bit * 57) >> 9, r9 = bit - q9 * 9, q3 = (r9 * 11) >> 5;      // bit / 9, bit % 9, (bit % 9) / 3
+            const int nz = q9 - 1, ny = q3 - 1, nx = r9 - q3 * 3 - 1;
+            const int ps = ((sz - nz) << 2) | ((sy - ny) << 1) | (sx - nx);
+            const int id = bit == 13 ? s_u[e] : cell_rank(bm, wp, cell + nz * s12 + ny * S2 + nx);
+            const int s0 = start[o + id], cnt = count[o + id];
+            for (int q = 0; q < cnt; ++q) {
+                const float4 rr = __ldg(rec + o + s0 + q);
+                const float r[3] = {rr.x, rr.y, rr.z};
+                const float m[3] = {__fsub_rn(1.0f, rr.x), __fsub_rn(1.0f, rr.y), __fsub_rn(1.0f, rr.z)};
+                acc = __fadd_rn(acc, corner_weight(r, m, ps));
             }
-            const int64_t v = (int64_t)cell + sz * s12 + sy * S2 + sx;
-            gmap[v] = vox_finish(acc, (int64_t)bb * vp.V + v, tail_start, sat_mask);
         }
+        const int64_t v = (int64_t)cell + sz * s12 + sy * S2 + sx;
+        grid[(int64_t)bb * vp.V + v] = vox_finish(acc, (int64_t)bb * vp.V + v, tail_start, sat_mask);
     }
 }
 
