@@ -353,8 +353,9 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
     // kinds are then compacted into two block-wide lists, and phases B / C walk them with consecutive threads: a warp runs
     // ONE of the two code paths on 32 cells of its kind.  (One thread per cell in index order made every warp that held a
     // single non-isolated cell pay for the general path -- 10 % of the cells at 256^3, a third of the warps' time.)
-    __shared__ int s_cell[256], s_map[256], s_u[256];
+    __shared__ int s_cell[256], s_map[256], s_start[256], s_cnt[256];
     __shared__ uint32_t s_occ[256];
+    __shared__ float4 s_rec0[256];                 // the cell's first record
     __shared__ uint16_t s_list[256 + 2048];        // isolated cells (thread index), then owned voxels (thread index << 3 | sh)
     __shared__ int s_wcnt[9][8], s_n[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -370,7 +371,12 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
     uint32_t occ = 0;
     if (valid) {
         const uint32_t *bm = bitmap + (size_t)b * vp.Wd;
+        // The cell's run (start, count: coalesced) and its first record are fetched HERE, next to the bitmap rows: phase B
+        // used to start with the dependent chain start/count -> record (ncu at 256^3: 44 % issue active, 16 stalled warps
+        // per issue on the long scoreboard, a third of them on these two loads).
         const int cell = cell_lin[(size_t)b * vp.N + u];
+        const int st0 = start[(size_t)b * vp.N + u], cn0 = count[(size_t)b * vp.N + u];
+        const float4 r0 = __ldg(rec + (size_t)b * vp.N + st0);
         // occupancy of the neighbourhood: bit ((dz+1)*3 + (dy+1))*3 + (dx+1)
         const int first = cell - s12 - S2 - 1;
         if (first >= 0 && (int64_t)cell + s12 + S2 + 34 <= (int64_t)vp.Wd * 32) {
@@ -403,7 +409,9 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
         }
         s_cell[tid] = cell;
         s_map[tid] = b;
-        s_u[tid] = u;
+        s_start[tid] = st0;
+        s_cnt[tid] = cn0;
+        s_rec0[tid] = r0;
         s_occ[tid] = occ;
     }
     // Compaction.  List 0: the isolated cells.  Lists 1..8: the voxels (cell, corner shift sh) that a general cell OWNS, shift
@@ -475,10 +483,10 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
         const int e = s_list[i], cell = s_cell[e], bb = s_map[e];
         const size_t o = (size_t)bb * vp.N;
         float *gmap = grid + (int64_t)bb * vp.V;
-        const int s_own = start[o + s_u[e]], c_own = count[o + s_u[e]];
+        const int s_own = s_start[e], c_own = s_cnt[e];
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int q = 0; q < c_own; ++q) {
-            const float4 rr = __ldg(rec + o + s_own + q);
+            const float4 rr = q == 0 ? s_rec0[e] : __ldg(rec + o + s_own + q);
             const float r[3] = {rr.x, rr.y, rr.z};
             const float m[3] = {__fsub_rn(1.0f, rr.x), __fsub_rn(1.0f, rr.y), __fsub_rn(1.0f, rr.z)};
 #pragma unroll
@@ -511,8 +519,12 @@ __global__ void __launch_bounds__(256) vox_accumulate_kernel(VoxParams vp, const
             const int q9 = (bit * 57) >> 9, r9 = bit - q9 * 9, q3 = (r9 * 11) >> 5;      // bit / 9, bit % 9, (bit % 9) / 3
             const int nz = q9 - 1, ny = q3 - 1, nx = r9 - q3 * 3 - 1;
             const int ps = ((sz - nz) << 2) | ((sy - ny) << 1) | (sx - nx);
-            const int id = bit == 13 ? s_u[e] : cell_rank(bm, wp, cell + nz * s12 + ny * S2 + nx);
-            const int s0 = start[o + id], cnt = count[o + id];
+            int s0 = s_start[e], cnt = s_cnt[e];
+            if (bit != 13) {
+                const int id = cell_rank(bm, wp, cell + nz * s12 + ny * S2 + nx);
+                s0 = start[o + id];
+                cnt = count[o + id];
+            }
             for (int q = 0; q < cnt; ++q) {
                 const float4 rr = __ldg(rec + o + s0 + q);
                 const float r[3] = {rr.x, rr.y, rr.z};
