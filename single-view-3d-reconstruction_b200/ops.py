@@ -570,8 +570,10 @@ class PackedDecoder:
         self.t = {}
         self.frozen = False
 
-    def get(self, pyr: PyramidSpec, w0, w1, w2):
-        key = (pyr.channels, pyr.align_corners, w0.data_ptr(), w1.data_ptr(), w2.data_ptr())
+    def get(self, pyr: PyramidSpec, w0, w1, w2, backward=True):
+        """``backward=False`` (inference): the swizzled images of the TRANSPOSED weights, which only the fused decoder
+        backward streams, are not built (three launches of the nine)."""
+        key = (pyr.channels, pyr.align_corners, w0.data_ptr(), w1.data_ptr(), w2.data_ptr(), bool(backward))
         if key != self.key or not self.frozen:
             dev = w0.device
             h0, h1, h2 = w0.shape[0], w1.shape[0], w2.shape[0]
@@ -586,7 +588,7 @@ class PackedDecoder:
             _abi.check(_lib().svr_pack_matrix(w1f.data_ptr(), h1, h0, t["w1"].data_ptr(), t["w1T"].data_ptr(), st), "pack_matrix")
             _abi.check(_lib().svr_pack_matrix(w2f.data_ptr(), h2, h1, t["w2"].data_ptr(), t["w2T"].data_ptr(), st), "pack_matrix")
             if h0 == h1 == h2 == 256:    # pre-swizzled UMMA chunk images for the fused forward kernel
-                for name in ("w0p", "w1", "w2", "w0pT", "w1T", "w2T"):
+                for name in ("w0p", "w1", "w2") + (("w0pT", "w1T", "w2T") if backward else ()):
                     t[name + "_img"] = swizzled_image(t[name])
             self.t, self.key = t, key
         return self.t
@@ -715,7 +717,7 @@ def dense_eval(pyr, cache, x, vols, w0, b0, w1, b1, w2, b2, wo, bo, lattice, sce
     sx, sy, sz = (int(v) for v in lattice)
     scenes = list(range(x0.shape[0])) if scenes is None else list(scenes)
     packed = [pack_volume(v) for v in vols]
-    W = cache.get(pyr, w0, w1, w2)
+    W = cache.get(pyr, w0, w1, w2, backward=False)
     if "w0p_img" not in W:
         raise RuntimeError("svr_b200: the fused dense evaluator needs a 256/256/256 decoder")
     b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
@@ -742,11 +744,12 @@ class QueryPrefetch:
         self.pyr, self.pts_key = pyr, (pts.data_ptr(), tuple(pts.shape))
         self._pts = pts                        # alive until the consumer has waited on `event`
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        grad_enabled = torch.is_grad_enabled()
         ev = main.record_event()               # the points / weights are ready in main-stream order
         with torch.cuda.device(dev), torch.cuda.stream(side), torch.autocast("cuda", enabled=False):
             side.wait_event(ev)
             self.perm = sort_points(pts) if pts.shape[1] >= SORT_MIN_POINTS else None
-            self.W = cache.get(pyr, w0, w1, w2)
+            self.W = cache.get(pyr, w0, w1, w2, backward=grad_enabled)
             self.event = side.record_event()
         for t in ([self.perm] if self.perm is not None else []) + list(self.W.values()):
             t.record_stream(main)
@@ -777,13 +780,15 @@ class _Query(torch.autograd.Function):
             torch.cuda.current_stream(dev).wait_event(prefetched.event)
             W = prefetched.W
         else:
-            W = cache.get(pyr, w0, w1, w2)
+            W = cache.get(pyr, w0, w1, w2, backward=bool(grad_mode))
         h0n, h1n, h2n = w0.shape[0], w1.shape[0], w2.shape[0]
         b0f, b1f, b2f, bof = (_dev_f32(b.detach(), "bias") for b in (b0, b1, b2, bo))
         wof = _dev_f32(wo.detach().reshape(-1), "fc_out.weight")
         # needs_input_grad is set for parameters even under torch.no_grad(); nothing is saved (and the kernels skip the
         # 1.3 GB of feature / activation stores per 200k points) unless a graph is being recorded
         needs_bwd = bool(grad_mode) and any(ctx.needs_input_grad)
+        if needs_bwd and "w0p_img" in W and "w0pT_img" not in W:      # prefetched without gradients enabled
+            W = cache.get(pyr, w0, w1, w2, backward=True)
         perm = None
         if USE_FUSED and "w0p_img" in W:
             if prefetched is not None:

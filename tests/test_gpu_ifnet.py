@@ -424,9 +424,18 @@ def test_first_stage_fused_conv_relu_bn(shape, zero_gamma):
         B, D, H, W = shape
         g = torch.Generator().manual_seed(sum(shape))
         x = (torch.rand((B, 1, D, H, W), generator=g) < 0.3).float().cuda()
+        torch.manual_seed(sum(shape))        # the modules' default initialisation draws from the global generator
         conv = torch.nn.Conv3d(1, 16, 3, padding=1).cuda()
         bn = torch.nn.BatchNorm3d(16).cuda()
         with torch.no_grad():
+            # keep every pre-activation away from the ReLU kink: on an occupancy grid a pre-activation is a sum of a subset
+            # of the 27 taps, and a draw that lands within 1e-6 of zero flips the ReLU mask between fp32 and the fp64 truth
+            # (seen once: fused stage AND cuDNN both 1.05e-3 off the fp64 gradient, min |pre-activation| 9.6e-7)
+            for _ in range(16):
+                pre = torch.nn.functional.conv3d(x.double(), conv.weight.double(), conv.bias.double(), padding=1)
+                if float(pre.abs().min()) > 1e-4:
+                    break
+                conv.bias.add_(3.1e-4)
             bn.weight.copy_(torch.rand(16, generator=g) + 0.5)
             bn.bias.copy_(torch.randn(16, generator=g) * 0.1)
             if zero_gamma:       # a BN scale of exactly 0 cannot be inverted: the backward falls back to recomputing relu(conv(x))
