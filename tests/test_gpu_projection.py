@@ -133,6 +133,22 @@ def test_blur_forward_backward_golden(golden):
         np.testing.assert_allclose(pts.grad.cpu().numpy(), g[f"{tag}_dpts"], rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 7, 128), (1, 3, 9, 260), (3, 1, 4, 4), (1, 17, 6, 384), (2, 40, 10, 112),
+                                   (1, 64, 8, 128), (1, 70, 3, 516), (2, 6, 5, 30)])
+def test_blur_333_shapes_against_oracle(shape):
+    """The 3x3x3 blur on grids that exercise both kernels: W % 4 == 0 runs the register-only warp kernel (single and
+    several 128-wide x tiles with edge halos, partial tiles, H not a multiple of the 4 rows a warp owns, z cut into
+    segments when there are few columns, D = 1), W = 30 the block kernel.  Tolerance 1e-6 abs (test module header)."""
+    B, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    vox = (torch.rand((B, D, H, W), generator=g) * 1.2).clamp(0, 1)     # includes saturated voxels
+    proj = _proj((D, H, W), (3, 3, 3), (1.5, 0.9, 2.1))
+    got = proj.voxels_smooth(vox.cuda(), proj.smoothing_kernel())
+    want = R.voxels_smooth(vox, R.smoothing_kernels(torch.tensor([1.5, 0.9, 2.1]), [3, 3, 3]))
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), atol=1e-6, rtol=0)
+
+
 def test_depth_gradient_matches_oracle_autograd():
     dims = (70, 52, 56)
     proj = _proj(dims)
