@@ -280,36 +280,40 @@ def config_block(config: int, world: int):
 # ------------------------------------------------------------------------------------------------
 # rooflines (SURVEY.md 8(d) figures)
 # ------------------------------------------------------------------------------------------------
-def _ncu_traffic(kernel_substr: str, files=("r2b_query_path.txt", "r2_query_path.txt", "r2_projection.txt", "r1_query_path_v4.txt")):
-    """dram read + write bytes per launch of a kernel from the newest committed `ncu --set full` summary (profiles/)."""
+def _ncu_traffic(kernel_substr: str, files=("r2c_projection.txt", "r2b_query_path.txt", "r2_query_path.txt", "r2_projection.txt", "r1_query_path_v4.txt"),
+                 occurrence: int = 0):
+    """dram read + write bytes per launch of a kernel from the newest committed `ncu --set full` summary (profiles/);
+    `occurrence` picks the n-th capture of that kernel in the file (the projection summaries hold the 128^3 capture first,
+    then the 256^3 one)."""
     unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "Tbyte": 1e12}
     for fname in files:
         f = ROOT / "profiles" / fname
         if not f.exists():
             continue
+        found = []
         cur, rd, wr = False, None, None
-        for line in f.read_text().splitlines():
+        for line in f.read_text().splitlines() + ["== kernel <end>"]:
             if line.startswith("== kernel"):
                 if cur and rd is not None and wr is not None:
-                    break
-                cur = kernel_substr in line
+                    found.append(rd + wr)
+                cur, rd, wr = kernel_substr in line, None, None
             elif cur and line.startswith("dram__bytes_read.sum "):
                 v = line.split()
                 rd = float(v[-2]) * unit.get(v[-1], 1.0)
             elif cur and line.startswith("dram__bytes_write.sum "):
                 v = line.split()
                 wr = float(v[-2]) * unit.get(v[-1], 1.0)
-        if rd is not None and wr is not None:
-            return rd + wr, f"profiles/{fname}"
+        if len(found) > occurrence:
+            return found[occurrence], f"profiles/{fname}"
     return None, None
 
 
-def _roof(kernel, ms, calls, bound, work, peaks, ncu_name=None, note=None):
+def _roof(kernel, ms, calls, bound, work, peaks, ncu_name=None, note=None, occurrence=0):
     """One roofline record.  `work` = algorithmic FLOPs (tensor) or bytes (hbm) of ALL launches of the kernel in one step,
     `ms` their summed duration: achieved = work / ms."""
     peak = peaks["bf16_tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"]
     ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
-    traffic, src = _ncu_traffic(ncu_name) if ncu_name else (None, None)
+    traffic, src = _ncu_traffic(ncu_name, occurrence=occurrence) if ncu_name else (None, None)
     r = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
          "frac": ach / peak, "traffic": traffic, "ms_per_step": ms, "launches_per_step": calls,
          "algorithmic_" + ("flops" if bound == "tensor" else "bytes") + "_per_step": work,
@@ -703,11 +707,13 @@ def run_config3(ctx):
             kms = ctx.kernel_pass(lambda i: step(depth), min(args.steps, 5))
         grid_bytes = B * S ** 3 * 4
         roofs = []
-        for key, work, ncu, note in (("svr_voxelize_fwd", grid_bytes + B * P * 12, "vox_accumulate_kernel", "7 launches (bucket, rank, accumulate ...) timed together: points in + grid written once"),
-                                     ("svr_blur_fwd", 2 * grid_bytes, "blur_fused333_kernel", "grid read once + written once"),
+        for key, work, ncu, note in (("svr_voxelize_fwd", grid_bytes + B * P * 12, "vox_accumulate_kernel",
+                                      "9 launches + 2 fills (mark, scans, count, fill, rank, accumulate) timed together: points in + grid written "
+                                      "once; traffic = the accumulate launch alone"),
+                                     ("svr_blur_fwd", 2 * grid_bytes, "blur_rows333_kernel", "grid read once + written once"),
                                      ("svr_unproject_fwd", B * P * 16, "unproject", "depth in + points out")):
             if key in kms:
-                roofs.append(_roof(key, kms[key][1], 1, "hbm", work, peaks, ncu, note))
+                roofs.append(_roof(key, kms[key][1], 1, "hbm", work, peaks, ncu, note, occurrence=0 if S == 128 else 1))
         roofs.sort(key=lambda r: -r["ms_per_step"])
         if S == 128 and rank == 0:
             clk = ctx.clocks.stop()
