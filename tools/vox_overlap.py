@@ -9,7 +9,14 @@ from torch.profiler import profile, ProfilerActivity
 S, B = (int(sys.argv[1]) if len(sys.argv) > 1 else 256), 64
 scale = 1 if S == 128 else 0.5
 proj = svr_b200.project((S, S, S), [3, 3, 3], torch.tensor([1.5, 1.5, 1.5])).cuda()
-depth = (torch.rand((B, 256, 256)) * 5.0 + 0.5).cuda()
+if len(sys.argv) > 2 and sys.argv[2] == "smooth":
+    # a smooth surface per map (a tilted, gently waving sheet): neighbouring pixels land in neighbouring cells, no cell is
+    # isolated -- the opposite extreme of the iid-random depths of BASELINE's synthetic configuration
+    v, u = torch.meshgrid(torch.linspace(0, 1, 256), torch.linspace(0, 1, 256), indexing="ij")
+    ph = torch.arange(B).view(B, 1, 1) * 0.37
+    depth = (2.5 + 0.8 * u + 0.5 * torch.sin(6.0 * v + ph) + 0.3 * torch.cos(9.0 * u - ph)).cuda()
+else:
+    depth = (torch.rand((B, 256, 256)) * 5.0 + 0.5).cuda()
 with torch.no_grad():
     pts = proj.depthmap_to_normed_points(depth, scale)
     for _ in range(3):
