@@ -85,3 +85,25 @@ def test_precision_switch_controls_tf32_and_restores_it():
     assert torch.backends.cudnn.allow_tf32 is False
     svr_b200.configure(precision=16)
     assert torch.backends.cudnn.allow_tf32 == before
+
+
+@pytest.mark.parametrize("ks", [(3, 3, 3), (5, 5, 5), (5, 3, 7)])
+def test_smoothing_kernel_matches_reference_recipe(ks):
+    """project.smoothing_kernel (projection.py:82-100): three normalised 1-D Gaussians of sigma.  Equal tap counts take the
+    batched (3, k) evaluation, mixed ones the per-axis loop: taps and d(taps)/d(sigma) must equal the oracle's restatement
+    of the reference recipe bit for bit (pure torch ops, so this runs on the CPU)."""
+    import torch
+    import svr_b200
+    from oracle import ref_torch as R
+    sig = torch.tensor([1.5, 0.9, 2.1])
+    proj = svr_b200.project((16, 12, 20), list(ks), sig.clone())
+    mine = proj.smoothing_kernel()
+    s_ref = sig.clone().requires_grad_(True)
+    want = R.smoothing_kernels(s_ref, list(ks))
+    assert [tuple(t.shape) for t in mine] == [tuple(t.shape) for t in want]
+    cot = [torch.linspace(0.3, 1.7, k) for k in ks]
+    for a in range(3):
+        assert torch.equal(mine[a].detach(), want[a].detach()), a
+    sum((m.reshape(-1) * c).sum() for m, c in zip(mine, cot)).backward()
+    sum((w.reshape(-1) * c).sum() for w, c in zip(want, cot)).backward()
+    torch.testing.assert_close(proj.sigma.grad, s_ref.grad, rtol=1e-6, atol=1e-7)
