@@ -16,7 +16,7 @@
 namespace svr {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int GEMM_THREADS = 288;

@@ -310,7 +310,6 @@ __device__ __forceinline__ uint4 gather_unit_fast(const UnitCtx &c, int align, f
             w[k] = wxy[k & 3] * ((k & 4) ? wz1 : wz0);
         }
     } else {
-#pragma unroll
         const bool vx[2] = {(unsigned)x0 < (unsigned)c.W, (unsigned)(x0 + 1) < (unsigned)c.W};
         const bool vy[2] = {(unsigned)y0 < (unsigned)c.H, (unsigned)(y0 + 1) < (unsigned)c.H};
         const bool vz[2] = {(unsigned)z0 < (unsigned)c.D, (unsigned)(z0 + 1) < (unsigned)c.D};
