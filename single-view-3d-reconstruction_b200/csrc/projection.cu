@@ -275,13 +275,14 @@ __global__ void vox_count_kernel(VoxParams vp, const int *__restrict__ cell_of_p
 // is alone in its cell here, with K6 skipping it, was slower: fill 48 -> 75 us, rank 69 -> 65 us at 128^3 -- the scattered
 // 16-byte record stores, not the cursor atomics, are what both kernels wait on.)
 __global__ void vox_fill_kernel(VoxParams vp, const int *__restrict__ cid_of_point, const int *__restrict__ start,
-                                int *__restrict__ cursor, int *__restrict__ order) {
+                                const int *__restrict__ count, int *__restrict__ cursor, int *__restrict__ order) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)vp.B * vp.N) return;
     int b = (int)(i / vp.N), n = (int)(i % vp.N);
     int id = cid_of_point[i];
     if (id < 0) return;
     size_t o = (size_t)b * vp.N;
+    if (count[o + id] == 1) return;          // alone in its cell: rank 0, K6 needs no list (one load instead of an atomic + a store)
     int slot = start[o + id] + atomicAdd(cursor + o + id, 1);
     order[o + slot] = n;
 }
@@ -300,7 +301,8 @@ __global__ void vox_rank_kernel(const float *__restrict__ pts, VoxParams vp, con
     size_t o = (size_t)b * vp.N;
     int s = start[o + id], c = count[o + id];
     int rank = 0;
-    for (int t = 0; t < c; ++t) rank += (order[o + s + t] < n);
+    if (c > 1)
+        for (int t = 0; t < c; ++t) rank += (order[o + s + t] < n);
     int f[3];
     float r[3], m[3];
     point_frac(pts + i * 3, vp, f, r, m);
@@ -1132,7 +1134,7 @@ int svr_voxelize_fwd(const float *pts, int B, int N, const int64_t *dims3_host, 
     scan_blocks_kernel<1><<<(unsigned)(B * nblk_n), SCAN_THREADS, 0, st>>>((const uint32_t *)w.count, (uint32_t *)w.start, N, w.ucount, N, nblk_n,
                                                                           w.bsum, nullptr);
     SVR_LAUNCH_CHECK();
-    vox_fill_kernel<<<gp, 256, 0, st>>>(vp, w.cid_of_point, w.start, w.cursor, w.order);
+    vox_fill_kernel<<<gp, 256, 0, st>>>(vp, w.cid_of_point, w.start, w.count, w.cursor, w.order);
     SVR_LAUNCH_CHECK();
     vox_rank_kernel<<<gp, 256, 0, st>>>(pts, vp, w.cid_of_point, w.start, w.count, w.order, w.rec);
     SVR_LAUNCH_CHECK();
