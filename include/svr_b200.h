@@ -77,7 +77,7 @@ int svr_voxelize_bwd(const float *pts, const float *grad_grid, const uint32_t *s
 /* project.voxels_smooth (projection.py:102-117): three zero-padded 1-D cross-correlations (taps_w
  * on the last axis, taps_h on the middle one, taps_d on the first), then clamp(0,1).
  * The taps are DEVICE arrays (no host sync).  tmp0/tmp1: two scratch grids of the same size as
- * `in`.  Odd tap counts <= SVR_MAX_TAPS.                                                         */
+ * `in`.  Odd tap counts <= SVR_MAX_TAPS.  `out` must not alias `in`.                             */
 int svr_blur_fwd(const float *in, int B, int D, int H, int W, const float *taps_w, int kw,
                  const float *taps_h, int kh, const float *taps_d, int kd, float *out,
                  float *tmp0, float *tmp1, void *stream);

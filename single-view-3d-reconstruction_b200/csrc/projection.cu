@@ -1163,6 +1163,7 @@ static int check_taps(const float *t, int k) {
 int svr_blur_fwd(const float *in, int B, int D, int H, int W, const float *taps_w, int kw, const float *taps_h, int kh,
                  const float *taps_d, int kd, float *out, float *tmp0, float *tmp1, void *stream) {
     SVR_REQUIRE(in && out && tmp0 && tmp1, "blur: null pointer");
+    SVR_REQUIRE(in != out, "blur: in-place operation is not supported (every output voxel reads its input neighbours)");
     if (int rc = check_taps(taps_w, kw)) return rc;
     if (int rc = check_taps(taps_h, kh)) return rc;
     if (int rc = check_taps(taps_d, kd)) return rc;
