@@ -97,6 +97,25 @@ def test_voxelize_vs_oracle_seeded(case, dims):
         assert float(got.sum()) == 0.0
 
 
+@pytest.mark.parametrize("hw", [(37, 50), (21, 33), (16, 68), (1, 4)])
+def test_unproject_widths_bit_exact(hw):
+    """Depth maps whose width is / is not a multiple of 4 (the 4-pixels-per-thread kernel and the scalar one), grid space
+    and normalised: bit-exact against the plain-C oracle."""
+    H, W = hw
+    dims = (70, 52, 56)
+    g = torch.Generator().manual_seed(H * 100 + W)
+    depth = torch.rand((3, H, W), generator=g) * 6.0 + 0.3
+    proj = _proj(dims)
+    _, c2f = R.frustum_transform(R.intrinsic_matrix(), 1)
+    a = [float(c2f[k, k]) for k in range(3)]
+    t = [float(c2f[k, 3]) for k in range(3)]
+    f, cx, cy = np.float32(R.FOCAL), np.float32(R.CX), np.float32(R.CY)
+    want_grid = CO.unproject(depth.numpy(), f, cx, cy, a, t, dims, norm=False)
+    want_norm = CO.unproject(depth.numpy(), f, cx, cy, a, t, dims, norm=True)
+    assert np.array_equal(_bits(proj.depthmap_to_gridspace(depth.cuda(), 1)), want_grid.view(np.uint32))
+    assert np.array_equal(_bits(proj.depthmap_to_normed_points(depth.cuda(), 1)), want_norm.view(np.uint32))
+
+
 def test_voxelize_direct_points_and_ragged():
     dims = (24, 20, 28)
     proj = _proj(dims)
