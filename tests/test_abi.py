@@ -107,3 +107,44 @@ def test_smoothing_kernel_matches_reference_recipe(ks):
     sum((m.reshape(-1) * c).sum() for m, c in zip(mine, cot)).backward()
     sum((w.reshape(-1) * c).sum() for w, c in zip(want, cot)).backward()
     torch.testing.assert_close(proj.sigma.grad, s_ref.grad, rtol=1e-6, atol=1e-7)
+
+
+def test_voxeliser_ownership_masks_match_their_definition():
+    """csrc/projection.cu hard-codes two constant tables for the accumulate pass (neighbourhood bit ((dz+1)*3 + (dy+1))*3 +
+    (dx+1) of the source cell of pass ps for the voxel at corner shift sh).  Re-derive them from the definition
+    (projection.py:69-78: pass ps adds to the voxel at floor + ps, so the voxel cell+sh receives pass ps from the cell
+    cell + sh - ps) and check the magic-number divisions by 9 and 3 that decode a bit index."""
+    src = (REPO / "single-view-3d-reconstruction_b200" / "csrc" / "projection.cu").read_text()
+
+    def table(name):
+        m = re.search(name + r"\[8\]\s*=\s*\{([^}]*)\}", src)
+        assert m, name
+        return [int(v.strip().rstrip("u"), 16) for v in m.group(1).split(",")]
+
+    lower, srcs = [], []
+    for sh in range(8):
+        lo = sr = 0
+        for ps in range(8):
+            n = [((sh >> k) & 1) - ((ps >> k) & 1) for k in (2, 1, 0)]          # (dz, dy, dx) of the source cell
+            bit = ((n[0] + 1) * 3 + (n[1] + 1)) * 3 + (n[2] + 1)
+            if ps < sh:
+                lo |= 1 << bit
+            else:
+                sr |= 1 << bit
+        lower.append(lo)
+        srcs.append(sr)
+    assert table("c_vox_lower") == lower
+    assert table("c_vox_src") == srcs
+    for bit in range(27):
+        q9 = (bit * 57) >> 9
+        r9 = bit - q9 * 9
+        q3 = (r9 * 11) >> 5
+        assert (q9, r9, q3) == (bit // 9, bit % 9, r9 // 3)
+    # a higher bit is an earlier pass for every shift: walking the set bits downwards is the reference's pass order
+    for sh in range(8):
+        order = []
+        for bit in range(26, -1, -1):
+            if (srcs[sh] >> bit) & 1:
+                nz, ny, nx = bit // 9 - 1, (bit % 9) // 3 - 1, bit % 3 - 1
+                order.append(((((sh >> 2) & 1) - nz) << 2) | ((((sh >> 1) & 1) - ny) << 1) | ((sh & 1) - nx))
+        assert order == sorted(order) and order[0] == sh
