@@ -1,4 +1,5 @@
-"""svr_blur_fwd (3x3x3) on 64 grids of S^3: ms per call; argv[1] = S.  SVR_BLUR_ZSPLIT overrides the z split (probe)."""
+"""svr_blur_fwd (3x3x3) on 64 grids of S^3: ms per call and GB/s of compulsory traffic; argv[1] = S.  (The z-split sweep
+recorded in csrc/projection.cu / DESIGN.md 4.2 was run with a temporary override of `zsplit` in svr_blur_fwd.)"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
